@@ -1,0 +1,105 @@
+// Library context, error plumbing and device workspace shared by every .cu of libb200g16.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200g16.h"
+
+namespace b200 {
+
+// thread-local last error (errors cross the C-ABI as int + string)
+inline char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define B200_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::b200::fail(B200G16_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,    \
+                          cudaGetErrorString(_e));                                          \
+  } while (0)
+
+#define B200_TRY(expr)          \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != 0) return _s;     \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) B200_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    B200_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct MsmWorkspace {
+  DevBuf scalars, digits, entries, counts, partials, buckets, chunks, windows, misc, tasks;
+  void* pinned = nullptr;  // small host staging for window sums
+  size_t pinned_cap = 0;
+};
+
+struct NttWorkspace {
+  DevBuf a, b, c, tw;
+  int tw_log = -1;
+};
+
+struct Timings {
+  // last-call device timings in ms (CUDA events on ctx stream); index = phase
+  float ms[16];
+  int n;
+};
+
+}  // namespace b200
+
+struct b200g16_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[18] = {};
+  std::mutex mu;  // one call at a time per ctx (gnark calls MSMs from several goroutines)
+  b200::MsmWorkspace msm;
+  b200::NttWorkspace ntt;
+  b200::DevBuf io_a, io_b, io_c;  // staging for host-pointer entry points
+  b200::Timings timings = {};
+  int msm_window_override = 0;  // 0 = auto
+  uint64_t launches = 0;        // kernels launched by this ctx (bench's gpu_launches)
+};
+
+struct b200g16_bases {
+  int group = 1;  // 1 = G1, 2 = G2
+  size_t n = 0;
+  void* d_points = nullptr;
+  int device = 0;
+};

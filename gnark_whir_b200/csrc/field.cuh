@@ -1,0 +1,207 @@
+// 254-bit prime-field arithmetic in Montgomery form (R = 2^256), 8 x 32-bit limbs.
+//
+// Memory layout is gnark-crypto's fp.Element / fr.Element ([4]uint64 little-endian limbs,
+// Montgomery form) reinterpreted as 8 little-endian uint32 — byte-identical on x86-64 and
+// on the GPU, so Go slices can be handed to the C-ABI untouched (the reference
+// shows the 4xu64 LE limb convention at main.go:19-21 and typeConverters.go:26-44).
+//
+// mul(): word-serial Montgomery product with interleaved reduction, organised as two
+// carry chains over 64-bit-aligned column pairs ("even"/"odd" accumulators) so that every
+// 32x32 partial product is one mad.lo.cc/madc.hi.cc pair (one IMAD.WIDE on sm_100a) and no
+// partial product ever needs a separate carry fix-up: 2*8*8 + 8 = 136 multiply-adds.
+#pragma once
+#include "bn254_constants.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct FpTag {
+  static constexpr uint32_t INV = FpParams::INV;
+  static B200_HD constexpr uint32_t mod(int i) { constexpr uint32_t m[8] = B200_FP_MOD; return m[i]; }
+  static B200_HD constexpr uint32_t one(int i) { constexpr uint32_t m[8] = B200_FP_ONE; return m[i]; }
+  static B200_HD constexpr uint32_t r2(int i) { constexpr uint32_t m[8] = B200_FP_R2; return m[i]; }
+};
+struct FrTag {
+  static constexpr uint32_t INV = FrParams::INV;
+  static B200_HD constexpr uint32_t mod(int i) { constexpr uint32_t m[8] = B200_FR_MOD; return m[i]; }
+  static B200_HD constexpr uint32_t one(int i) { constexpr uint32_t m[8] = B200_FR_ONE; return m[i]; }
+  static B200_HD constexpr uint32_t r2(int i) { constexpr uint32_t m[8] = B200_FR_R2; return m[i]; }
+};
+
+template <class T>
+struct alignas(16) Field {
+  static constexpr int N = 8;
+  uint32_t l[N];
+
+  static B200_HD Field zero() { Field r; for (int i = 0; i < N; i++) r.l[i] = 0; return r; }
+  static B200_HD Field one() { Field r; for (int i = 0; i < N; i++) r.l[i] = T::one(i); return r; }
+  static B200_HD Field modulus() { Field r; for (int i = 0; i < N; i++) r.l[i] = T::mod(i); return r; }
+  static B200_HD Field rsquared() { Field r; for (int i = 0; i < N; i++) r.l[i] = T::r2(i); return r; }
+
+  B200_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i];
+    return o == 0;
+  }
+  B200_HD bool operator==(const Field& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+    return o == 0;
+  }
+  B200_HD bool operator!=(const Field& b) const { return !(*this == b); }
+
+  // r = a - p if a >= p  (a < 2p)
+  static B200_HD void reduce_once(Field& a) {
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(a.l[0], T::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(a.l[i], T::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);  // 0 or 0xffffffff
+#pragma unroll
+    for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+  }
+
+  static B200_HD Field add(const Field& a, const Field& b) {
+    Field r;
+    r.l[0] = ptx::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(a.l[i], b.l[i]);
+    r.l[N - 1] = ptx::addc(a.l[N - 1], b.l[N - 1]);  // p < 2^254: no carry out
+    reduce_once(r);
+    return r;
+  }
+  static B200_HD Field dbl(const Field& a) { return add(a, a); }
+
+  static B200_HD Field sub(const Field& a, const Field& b) {
+    Field r;
+    r.l[0] = ptx::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r.l[i] = ptx::subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = ptx::subc(0, 0);
+    r.l[0] = ptx::add_cc(r.l[0], T::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(r.l[i], T::mod(i) & borrow);
+    r.l[N - 1] = ptx::addc(r.l[N - 1], T::mod(N - 1) & borrow);
+    return r;
+  }
+  static B200_HD Field neg(const Field& a) {
+    if (a.is_zero()) return a;
+    Field r;
+    r.l[0] = ptx::sub_cc(T::mod(0), a.l[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::subc_cc(T::mod(i), a.l[i]);
+    r.l[N - 1] = ptx::subc(T::mod(N - 1), a.l[N - 1]);
+    return r;
+  }
+
+  // ---- Montgomery product ------------------------------------------------------------
+  // acc[j],acc[j+1] = a[j]*bi for even j (independent wide products)
+  static B200_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      acc[j] = ptx::mul_lo(a[j], bi);
+      acc[j + 1] = ptx::mul_hi(a[j], bi);
+    }
+  }
+  // acc[j],acc[j+1] += a[j]*bi for even j, one carry chain; carry-out left in CC
+  static B200_HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+    acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+    }
+  }
+  // same chain against the compile-time modulus limbs (offset 0 or 1)
+  template <int OFF>
+  static B200_HD void cmad_mod(uint32_t* acc, uint32_t mi) {
+    acc[0] = ptx::mad_lo_cc(T::mod(OFF), mi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(T::mod(OFF), mi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = ptx::madc_lo_cc(T::mod(OFF + j), mi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(T::mod(OFF + j), mi, acc[j + 1]);
+    }
+  }
+  // acc[j],acc[j+1] = a[j]*bi + acc[j+2],acc[j+3] (+ carry-in from CC); top pair gets 0
+  static B200_HD void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j + 2]);
+      acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 3]);
+    }
+    acc[N - 2] = ptx::madc_lo_cc(a[N - 2], bi, 0);
+    acc[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
+  }
+  // One word of b: lo holds columns 0,1,..,7 (weights 2^(32k)), hi holds columns 1..8
+  // (weights 2^(32(k+1))) from the PREVIOUS word, i.e. one limb ahead; after the call the
+  // roles swap (the implicit divide-by-2^32).
+  template <bool FIRST>
+  static B200_HD void mad_n_redc(uint32_t* lo, uint32_t* hi, const uint32_t* a, uint32_t bi) {
+    if (FIRST) {
+      mul_n(hi, a + 1, bi);
+      mul_n(lo, a, bi);
+    } else {
+      lo[0] = ptx::add_cc(lo[0], hi[1]);
+      madc_n_rshift(hi, a + 1, bi);
+      cmad_n(lo, a, bi);
+      hi[N - 1] = ptx::addc(hi[N - 1], 0);
+    }
+    uint32_t mi = ptx::mul_lo(lo[0], T::INV);
+    cmad_mod<1>(hi, mi);
+    cmad_mod<0>(lo, mi);
+    hi[N - 1] = ptx::addc(hi[N - 1], 0);
+  }
+
+  static B200_HD Field mul(const Field& a, const Field& b) {
+    uint32_t even[N], odd[N];
+    mad_n_redc<true>(even, odd, a.l, b.l[0]);
+    mad_n_redc<false>(odd, even, a.l, b.l[1]);
+#pragma unroll
+    for (int i = 2; i < N; i += 2) {
+      mad_n_redc<false>(even, odd, a.l, b.l[i]);
+      mad_n_redc<false>(odd, even, a.l, b.l[i + 1]);
+    }
+    Field r;
+    r.l[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(even[i], odd[i + 1]);
+    r.l[N - 1] = ptx::addc(even[N - 1], 0);
+    reduce_once(r);
+    return r;
+  }
+  static B200_HD Field sqr(const Field& a) { return mul(a, a); }
+
+  // x*R^-1 (Montgomery -> canonical) and x*R (canonical -> Montgomery)
+  static B200_HD Field from_mont(const Field& a) {
+    Field o = zero();
+    o.l[0] = 1;
+    return mul(a, o);
+  }
+  static B200_HD Field to_mont(const Field& a) { return mul(a, rsquared()); }
+
+  // a^e for a canonical (non-Montgomery) exponent given as 8 limbs
+  static B200_HD_NOINLINE Field pow(const Field& a, const uint32_t* e) {
+    Field r = one();
+    for (int i = N * 32 - 1; i >= 0; i--) {
+      r = sqr(r);
+      if ((e[i >> 5] >> (i & 31)) & 1) r = mul(r, a);
+    }
+    return r;
+  }
+  // Fermat inverse (0 -> 0)
+  static B200_HD Field inv(const Field& a) {
+    uint32_t e[N];
+    for (int i = 0; i < N; i++) e[i] = T::mod(i);
+    e[0] -= 2;  // both moduli end in ...47 / ...01: no borrow for Fp; Fr: 0xf0000001-2 ok
+    return pow(a, e);
+  }
+};
+
+using Fp = Field<FpTag>;
+using Fr = Field<FrTag>;
+
+}  // namespace b200

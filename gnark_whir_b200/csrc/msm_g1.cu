@@ -1,0 +1,5 @@
+// G1 instantiation of the MSM back half (see msm_impl.cuh).
+#include "msm_impl.cuh"
+namespace b200 {
+template int msm_device<Fp>(b200g16_ctx*, const Affine<Fp>*, const Fr*, size_t, Affine<Fp>*);
+}

@@ -1,0 +1,269 @@
+// Pippenger multi-scalar multiplication over BN254 G1 / G2 for sm_100a.
+//
+// Replaces gnark-crypto ecc/bn254/multiexp.go (*G1Affine).MultiExp / (*G2Affine).MultiExp,
+// which gnark's groth16 prover (backend/groth16/bn254/prove.go) calls for Ar, Bs1, Krs,
+// Krs2 (the H/Z term), Bs2 and the BSB22 Pedersen commitment; reached from the reference at
+// /root/reference/mt.go:496.  Only the result (the group element, in affine normal form) is
+// observable at that boundary, so the decomposition below is B200-first, not gnark's:
+//
+//   k_digits      scalar Montgomery->canonical, signed c-bit digits (partitionScalars' job),
+//                 per-(window,bucket) histogram
+//   k_scan        exclusive scan of the histogram -> entry offsets; buckets larger than `seg`
+//                 are split into several tasks (0/1-heavy witnesses put millions of points in
+//                 bucket "1" of window 0) -> task offsets
+//   k_scatter     window-major counting-sort scatter of (point index, sign) into bucket order;
+//                 one window's 4n bytes of targets stay resident in the 126 MB L2
+//   k_tasks       task -> bucket table
+//   k_accumulate  one thread per task: gathers its affine points with 128-bit loads, mixed
+//                 XYZZ adds (10 modmul) on the integer pipe; next point prefetched during the add
+//   k_merge(+heavy) sums the partials of split buckets
+//   k_reduce / k_reduce2  running-sum bucket reduction per window, in chunks, then a block tree
+//   host          Horner over the W window sums + one inversion -> affine
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace b200 {
+
+struct MsmCfg {
+  int c;          // window bits
+  int W;          // windows
+  uint32_t nbw;   // buckets per window = 2^(c-1)
+  uint32_t nb;    // W * nbw
+  uint32_t seg;   // max entries per accumulate task
+  uint32_t ch;    // buckets per reduce chunk
+  uint32_t nch;   // chunks per window
+};
+
+// msm_common.cu
+int msm_num_windows(int c);
+int msm_pick_window(size_t n);
+// digits + histogram + scan + scatter + task table on ctx->stream (4 kernels + 1 memset)
+int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
+                   uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
+                   uint32_t* entries, uint32_t* task_bucket, int* ev);
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p) {
+  constexpr int NV = sizeof(Affine<F>) / 16;
+  Affine<F> r;
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+  uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int k = 0; k < NV; k++) dst[k] = __ldg(src + k);
+  return r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ bases,
+                                                     const uint32_t* __restrict__ entries,
+                                                     const uint32_t* __restrict__ task_bucket,
+                                                     const uint32_t* __restrict__ offsets,
+                                                     const uint32_t* __restrict__ counts,
+                                                     const uint32_t* __restrict__ task_off,
+                                                     const uint32_t* __restrict__ totals, uint32_t seg,
+                                                     XYZZ<F>* __restrict__ partials) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= totals[1]) return;
+  uint32_t b = task_bucket[t];
+  uint32_t start = offsets[b] + (t - task_off[b]) * seg;
+  uint32_t bend = offsets[b] + counts[b];
+  uint32_t end = start + seg < bend ? start + seg : bend;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  uint32_t e = entries[start];
+  Affine<F> p = load_affine(bases + (e >> 1));
+  for (uint32_t i = start; i < end; i++) {
+    Affine<F> cur = p;
+    uint32_t ce = e;
+    if (i + 1 < end) {
+      e = entries[i + 1];
+      p = load_affine(bases + (e >> 1));
+    }
+    if (ce & 1) cur.y = F::neg(cur.y);
+    acc.madd(cur);
+  }
+  partials[t] = acc;
+}
+
+#define B200_MERGE_SERIAL_MAX 16u
+
+template <class F>
+__global__ void __launch_bounds__(128) k_merge(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ counts,
+                                                const uint32_t* __restrict__ task_off, uint32_t nb, uint32_t seg,
+                                                XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ totals,
+                                                uint32_t* __restrict__ heavy) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t nt = (counts[b] + seg - 1) / seg;
+  if (nt == 0) { buckets[b] = XYZZ<F>::inf(); return; }
+  uint32_t o = task_off[b];
+  if (nt > B200_MERGE_SERIAL_MAX) {
+    heavy[atomicAdd(&totals[2], 1u)] = b;
+    return;
+  }
+  XYZZ<F> acc = partials[o];
+  for (uint32_t t = 1; t < nt; t++) acc.add(partials[o + t]);
+  buckets[b] = acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_merge_heavy(const XYZZ<F>* __restrict__ partials,
+                                                      const uint32_t* __restrict__ counts,
+                                                      const uint32_t* __restrict__ task_off, uint32_t seg,
+                                                      XYZZ<F>* __restrict__ buckets,
+                                                      const uint32_t* __restrict__ totals,
+                                                      const uint32_t* __restrict__ heavy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  uint32_t nheavy = totals[2];
+  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    uint32_t b = heavy[h];
+    uint32_t nt = (counts[b] + seg - 1) / seg;
+    uint32_t o = task_off[b];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = threadIdx.x; t < nt; t += blockDim.x) acc.add(partials[o + t]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        acc.add(sm[threadIdx.x + s]);
+        sm[threadIdx.x] = acc;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[b] = acc;
+    __syncthreads();
+  }
+}
+
+// thread per (window, chunk): sum_{b in chunk} (b+1) * B_b via a running sum from the top
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ buckets, int W, uint32_t nbw, uint32_t ch,
+                                                 uint32_t nch, int cbits, XYZZ<F>* __restrict__ chunks) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint32_t)W * nch) return;
+  uint32_t w = g / nch, k = g % nch;
+  uint32_t lo = k * ch;
+  const XYZZ<F>* base = buckets + (size_t)w * nbw;
+  XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  for (uint32_t j = ch; j-- > 0;) {
+    running.add(base[lo + j]);
+    acc.add(running);
+  }
+  if (lo) {
+    running.mul_small(lo, cbits);
+    acc.add(running);
+  }
+  chunks[g] = acc;
+}
+
+// block per window: tree-sum the chunk results
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce2(const XYZZ<F>* __restrict__ chunks, uint32_t nch,
+                                                  XYZZ<F>* __restrict__ windows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  uint32_t w = blockIdx.x;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t k = threadIdx.x; k < nch; k += blockDim.x) acc.add(chunks[(size_t)w * nch + k]);
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      acc.add(sm[threadIdx.x + s]);
+      sm[threadIdx.x] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) windows[w] = acc;
+}
+
+// ------------------------------------------------------------------------------ host driver
+template <class F>
+int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, Affine<F>* out) {
+  if (n == 0) { *out = Affine<F>::inf(); return 0; }
+  if (n >= (1ull << 31)) return fail(B200G16_ERR_ARG, "msm: n=%zu too large", n);
+  MsmCfg cfg;
+  cfg.c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(n);
+  if (cfg.c < 2 || cfg.c > 24) return fail(B200G16_ERR_ARG, "msm: window %d out of range", cfg.c);
+  cfg.W = msm_num_windows(cfg.c);
+  cfg.nbw = 1u << (cfg.c - 1);
+  cfg.nb = cfg.nbw * (uint32_t)cfg.W;
+  if ((double)n * cfg.W >= 4.0e9) return fail(B200G16_ERR_ARG, "msm: n*W overflows 32-bit entry index");
+  size_t m_max = n * (size_t)cfg.W;
+  // task segment: a few times the mean bucket load, so uniform scalars give ~1 task per bucket
+  size_t mean = m_max / cfg.nb + 1;
+  cfg.seg = (uint32_t)(mean * 4 < 64 ? 64 : (mean * 4 > 8192 ? 8192 : mean * 4));
+  cfg.ch = cfg.nbw < 32 ? cfg.nbw : 32;
+  cfg.nch = cfg.nbw / cfg.ch;
+  size_t max_tasks = (size_t)cfg.nb + m_max / cfg.seg + 1;
+
+  MsmWorkspace& ws = ctx->msm;
+  B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
+  B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
+  B200_TRY(ws.counts.ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
+  B200_TRY(ws.misc.ensure(64 + (size_t)cfg.nb * sizeof(uint32_t)));   // totals[16] + heavy list
+  B200_TRY(ws.tasks.ensure(max_tasks * sizeof(uint32_t)));
+  B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
+  B200_TRY(ws.buckets.ensure((size_t)cfg.nb * sizeof(XYZZ<F>)));
+  B200_TRY(ws.chunks.ensure((size_t)cfg.W * cfg.nch * sizeof(XYZZ<F>)));
+  B200_TRY(ws.windows.ensure((size_t)cfg.W * sizeof(XYZZ<F>)));
+  if (ws.pinned_cap < 130 * sizeof(XYZZ<Fp2>)) {
+    if (ws.pinned) cudaFreeHost(ws.pinned);
+    B200_CUDA(cudaMallocHost(&ws.pinned, 130 * sizeof(XYZZ<Fp2>)));
+    ws.pinned_cap = 130 * sizeof(XYZZ<Fp2>);
+  }
+  if (cfg.W > 128) return fail(B200G16_ERR_ARG, "msm: too many windows");
+
+  uint32_t* counts = ws.counts.as<uint32_t>();
+  uint32_t* offsets = counts + cfg.nb;
+  uint32_t* cursor = offsets + cfg.nb;
+  uint32_t* task_off = cursor + cfg.nb;
+  uint32_t* totals = ws.misc.as<uint32_t>();
+  uint32_t* heavy = totals + 16;
+  int32_t* digits = ws.digits.as<int32_t>();
+  uint32_t* entries = ws.entries.as<uint32_t>();
+  uint32_t* task_bucket = ws.tasks.as<uint32_t>();
+  XYZZ<F>* partials = ws.partials.as<XYZZ<F>>();
+  XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>();
+  XYZZ<F>* chunks = ws.chunks.as<XYZZ<F>>();
+  XYZZ<F>* windows = ws.windows.as<XYZZ<F>>();
+  cudaStream_t st = ctx->stream;
+  uint32_t n32 = (uint32_t)n;
+  int ev = 0;
+  auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
+
+  B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
+                          task_bucket, &ev));
+  k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_bucket, offsets, counts, task_off,
+                                                         totals, cfg.seg, partials);
+  mark();
+  k_merge<F><<<cdiv(cfg.nb, 128), 128, 0, st>>>(partials, counts, task_off, cfg.nb, cfg.seg, buckets, totals, heavy);
+  k_merge_heavy<F><<<ctx->sm_count, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, counts, task_off, cfg.seg, buckets,
+                                                                       totals, heavy);
+  mark();
+  k_reduce<F><<<cdiv((size_t)cfg.W * cfg.nch, 128), 128, 0, st>>>(buckets, cfg.W, cfg.nbw, cfg.ch, cfg.nch, cfg.c,
+                                                                   chunks);
+  k_reduce2<F><<<cfg.W, 128, 128 * sizeof(XYZZ<F>), st>>>(chunks, cfg.nch, windows);
+  mark();
+  ctx->launches += 5;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(ws.pinned, windows, (size_t)cfg.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+
+  // Horner over windows on the host: acc = sum_w 2^(c w) * S_w
+  const XYZZ<F>* hw = reinterpret_cast<const XYZZ<F>*>(ws.pinned);
+  XYZZ<F> acc = hw[cfg.W - 1];
+  for (int w = cfg.W - 2; w >= 0; w--) {
+    for (int k = 0; k < cfg.c; k++) acc.dbl();
+    acc.add(hw[w]);
+  }
+  *out = acc.to_affine();
+  return 0;
+}
+
+}  // namespace b200

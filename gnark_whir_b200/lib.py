@@ -1,0 +1,219 @@
+"""ctypes binding of libb200g16.so — the same C-ABI a cgo shim binds (include/b200g16.h).
+
+This module is plumbing for tests / bench / the Python host mirror; it contains no
+arithmetic and NO fallback: if the shared library (built by __graft_entry__.build()) is
+missing, or no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200g16.so")
+
+DIF, DIT = 0, 1
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "b200g16_version": (C.c_int, []),
+    "b200g16_last_error": (C.c_char_p, []),
+    "b200g16_init": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "b200g16_destroy": (None, [_vp]),
+    "b200g16_launch_count": (C.c_uint64, [_vp]),
+    "b200g16_last_timings": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int]),
+    "b200g16_set_msm_window": (C.c_int, [_vp, C.c_int]),
+    "b200g16_bases_upload_g1": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_bases_upload_g2": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_bases_free": (None, [_vp]),
+    "b200g16_bases_len": (_sz, [_vp]),
+    "b200g16_bases_download": (C.c_int, [_vp, _sz, _sz, _vp]),
+    "b200g16_fixed_base_mul_g1": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "b200g16_fixed_base_mul_g2": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "b200g16_bases_from_scalars_g1": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_bases_from_scalars_g2": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_modmul_probe": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "b200g16_msm_g1": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_msm_g2": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_msm_g1_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_msm_g2_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
+    "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
+    "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
+    "b200g16_g2_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
+}
+
+
+def load():
+    """dlopen the library (raises if it has not been built — there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(status):
+    if status != 0:
+        raise B200Error(f"libb200g16 error {status}: {load().b200g16_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _u64(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+# ---- host-only helpers (no GPU needed) -----------------------------------------------------
+def g1_add(a, b):
+    out = np.zeros(8, dtype=np.uint64)
+    _check(load().b200g16_g1_add(_ptr(_u64(a)), _ptr(_u64(b)), _ptr(out)))
+    return out
+
+
+def g2_add(a, b):
+    out = np.zeros(16, dtype=np.uint64)
+    _check(load().b200g16_g2_add(_ptr(_u64(a)), _ptr(_u64(b)), _ptr(out)))
+    return out
+
+
+def g1_scalar_mul(p, k):
+    out = np.zeros(8, dtype=np.uint64)
+    _check(load().b200g16_g1_scalar_mul(_ptr(_u64(p)), _ptr(_u64(k)), _ptr(out)))
+    return out
+
+
+def g2_scalar_mul(p, k):
+    out = np.zeros(16, dtype=np.uint64)
+    _check(load().b200g16_g2_scalar_mul(_ptr(_u64(p)), _ptr(_u64(k)), _ptr(out)))
+    return out
+
+
+class Bases:
+    """Device-resident vector of affine points (one of the proving key's point arrays)."""
+
+    def __init__(self, ctx, handle, group, n):
+        self.ctx, self.handle, self.group, self.n = ctx, handle, group, n
+
+    def free(self):
+        if self.handle:
+            load().b200g16_bases_free(self.handle)
+            self.handle = None
+
+    def __len__(self):
+        return self.n
+
+    def download(self, offset=0, n=None):
+        n = self.n - offset if n is None else n
+        out = np.zeros((n, 8 if self.group == 1 else 16), dtype=np.uint64)
+        _check(load().b200g16_bases_download(self.handle, offset, n, _ptr(out)))
+        return out
+
+
+class Context:
+    """One per process per GPU (b200g16_init)."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        _check(load().b200g16_init(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            load().b200g16_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- bookkeeping
+    def launch_count(self):
+        return int(load().b200g16_launch_count(self.h))
+
+    def last_timings(self):
+        buf = (C.c_float * 16)()
+        n = load().b200g16_last_timings(self.h, buf, 16)
+        return [buf[i] for i in range(n)]
+
+    def set_msm_window(self, c):
+        _check(load().b200g16_set_msm_window(self.h, int(c)))
+
+    # -- bases
+    def upload_g1(self, points):
+        pts = _u64(points, 8)
+        h = _vp()
+        _check(load().b200g16_bases_upload_g1(self.h, _ptr(pts), pts.shape[0], C.byref(h)))
+        return Bases(self, h, 1, pts.shape[0])
+
+    def upload_g2(self, points):
+        pts = _u64(points, 16)
+        h = _vp()
+        _check(load().b200g16_bases_upload_g2(self.h, _ptr(pts), pts.shape[0], C.byref(h)))
+        return Bases(self, h, 2, pts.shape[0])
+
+    # -- fixed-base batch scalar multiplication (BatchScalarMultiplicationG1/G2)
+    def fixed_base_mul(self, base, scalars, group=1, resident=False):
+        lib = load()
+        words = 8 if group == 1 else 16
+        base = _u64(base).reshape(words)
+        sc = _u64(scalars, 4)
+        n = sc.shape[0]
+        if resident:
+            h = _vp()
+            fn = lib.b200g16_bases_from_scalars_g1 if group == 1 else lib.b200g16_bases_from_scalars_g2
+            _check(fn(self.h, _ptr(base), _ptr(sc), n, C.byref(h)))
+            return Bases(self, h, group, n)
+        out = np.zeros((n, words), dtype=np.uint64)
+        fn = lib.b200g16_fixed_base_mul_g1 if group == 1 else lib.b200g16_fixed_base_mul_g2
+        _check(fn(self.h, _ptr(base), _ptr(sc), n, _ptr(out)))
+        return out
+
+    def modmul_probe(self, blocks_per_sm=4, chains=4, iters=2000):
+        rate = C.c_double()
+        ms = C.c_float()
+        _check(load().b200g16_modmul_probe(self.h, blocks_per_sm, chains, iters, C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
+
+    # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
+    def msm(self, bases, scalars, offset=0, n=None):
+        lib = load()
+        words = 8 if bases.group == 1 else 16
+        out = np.zeros(words, dtype=np.uint64)
+        if isinstance(scalars, np.ndarray):
+            sc = _u64(scalars, 4)
+            n = sc.shape[0] if n is None else n
+            fn = lib.b200g16_msm_g1 if bases.group == 1 else lib.b200g16_msm_g2
+            _check(fn(self.h, bases.handle, offset, _ptr(sc), n, _ptr(out)))
+        else:  # raw device pointer (e.g. torch tensor .data_ptr())
+            fn = lib.b200g16_msm_g1_dev if bases.group == 1 else lib.b200g16_msm_g2_dev
+            _check(fn(self.h, bases.handle, offset, _vp(int(scalars)), n, _ptr(out)))
+        return out

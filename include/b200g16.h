@@ -1,0 +1,127 @@
+/* libb200g16 — C-ABI of the B200-native Groth16/BN254 prover hot path.
+ *
+ * This is the drop-in boundary behind the three calls the reference makes at
+ * /root/reference/mt.go:448 (groth16.Setup), mt.go:496 (groth16.Prove) and mt.go:497
+ * (groth16.Verify): a Go package with gnark's Prove signature runs the solver in Go and
+ * reaches everything after it through cgo into these entry points (INTEGRATION.md shows
+ * the cgo stub).  Each function names the gnark / gnark-crypto routine it replaces
+ * (gnark v0.11.0, gnark-crypto v0.14.1-0.20241217131346-b998989abdbe; go.mod:6-7 — the
+ * sources are not vendored in the reference, so citations are package/func names).
+ *
+ * Data layout (identical to gnark-crypto's in-memory layout, so Go passes
+ * unsafe.Pointer(&slice[0]) without repacking; the reference shows the same 4 x u64
+ * little-endian limb convention at main.go:19-21 and typeConverters.go:26-44):
+ *   fr.Element / fp.Element : uint64_t[4], little-endian limbs, MONTGOMERY form (R = 2^256)
+ *   G1Affine                : uint64_t[8]  = X, Y            ; infinity = all zero
+ *   G2Affine                : uint64_t[16] = X.A0, X.A1, Y.A0, Y.A1 ; infinity = all zero
+ * All outputs are affine and in Montgomery form.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200G16_ERR_* otherwise;
+ *     b200g16_last_error() returns a thread-local message for the last failure.
+ *   - host pointers are only read/written during the call and never retained
+ *     (cgo pointer rules); device memory is owned by the ctx / bases handles.
+ *   - a ctx is bound to one GPU; calls on one ctx are serialised internally, so it may
+ *     be used from any OS thread (goroutines).  One process per GPU for multi-GPU.
+ *   - there is NO CPU fallback: without a usable CUDA device b200g16_init fails.
+ */
+#ifndef B200G16_H
+#define B200G16_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200G16_OK 0
+#define B200G16_ERR_CUDA (-1)     /* a CUDA runtime call failed                       */
+#define B200G16_ERR_ARG (-2)      /* invalid argument                                 */
+#define B200G16_ERR_NO_DEVICE (-3)/* no CUDA device / wrong architecture (no fallback) */
+#define B200G16_ERR_STATE (-4)    /* handle used on the wrong ctx / after free        */
+
+#define B200G16_DIF 0 /* fft.DIF : natural-order input -> bit-reversed output */
+#define B200G16_DIT 1 /* fft.DIT : bit-reversed input -> natural-order output */
+
+typedef struct b200g16_ctx b200g16_ctx;
+typedef struct b200g16_bases b200g16_bases;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int b200g16_version(void);
+const char* b200g16_last_error(void);
+/* Bind a context to CUDA device `device` (one per process per GPU). */
+int b200g16_init(int device, b200g16_ctx** out);
+void b200g16_destroy(b200g16_ctx* ctx);
+/* Number of CUDA kernels this ctx has launched so far (bench.py's gpu_launches). */
+uint64_t b200g16_launch_count(const b200g16_ctx* ctx);
+/* Device time (ms, CUDA events on the ctx stream) of the phases of the last MSM /
+ * computeH call: writes up to `cap` floats, returns how many. */
+int b200g16_last_timings(const b200g16_ctx* ctx, float* out_ms, int cap);
+/* Force the Pippenger window width (0 = automatic). Testing / tuning only. */
+int b200g16_set_msm_window(b200g16_ctx* ctx, int c);
+
+/* ---- resident bases (the proving key's point vectors) ---------------------------- */
+/* Copies n affine points to the GPU once; replaces the lazy device copy gnark's icicle
+ * backend keeps beside groth16_bn254.ProvingKey.{G1.A,G1.B,G1.K,G1.Z,G2.B} and
+ * pedersen.ProvingKey.{Basis,BasisExpSigma}. */
+int b200g16_bases_upload_g1(b200g16_ctx* ctx, const uint64_t* points, size_t n, b200g16_bases** out);
+int b200g16_bases_upload_g2(b200g16_ctx* ctx, const uint64_t* points, size_t n, b200g16_bases** out);
+void b200g16_bases_free(b200g16_bases* bases);
+size_t b200g16_bases_len(const b200g16_bases* bases);
+
+/* Copy points [offset, offset+n) of a resident vector back to the host (tests / sampling). */
+int b200g16_bases_download(const b200g16_bases* bases, size_t offset, size_t n, uint64_t* out_points);
+
+/* ---- batch fixed-base scalar multiplication (Setup's hot loop) --------------------- */
+/* out_points[i] = scalars[i] * base.  Replaces gnark-crypto ecc/bn254
+ * BatchScalarMultiplicationG1 / BatchScalarMultiplicationG2 as used by gnark
+ * backend/groth16/bn254/setup.go (groth16.Setup, reference mt.go:448).
+ * scalars: n fr.Element (Montgomery), host.  out_points: n affine points, host. */
+int b200g16_fixed_base_mul_g1(b200g16_ctx* ctx, const uint64_t base[8], const uint64_t* scalars, size_t n,
+                              uint64_t* out_points);
+int b200g16_fixed_base_mul_g2(b200g16_ctx* ctx, const uint64_t base[16], const uint64_t* scalars, size_t n,
+                              uint64_t* out_points);
+/* Same, but the n results stay on the GPU as a new resident bases vector (Setup feeding
+ * Prove without a round trip through the host; synthetic 2^24-point workloads). */
+int b200g16_bases_from_scalars_g1(b200g16_ctx* ctx, const uint64_t base[8], const uint64_t* scalars, size_t n,
+                                  b200g16_bases** out);
+int b200g16_bases_from_scalars_g2(b200g16_ctx* ctx, const uint64_t base[16], const uint64_t* scalars, size_t n,
+                                  b200g16_bases** out);
+
+/* ---- integer-pipe probe -------------------------------------------------------------- */
+/* Runs `chains` independent Montgomery-multiply dependency chains of length `iters` in
+ * each of 128 x blocks_per_sm x #SM threads and reports modmul/s: the measured
+ * integer-pipe roofline denominator for MSM / NTT (136 multiply-adds per modmul). */
+int b200g16_modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, double* modmul_per_s,
+                         float* ms);
+
+/* ---- multi-scalar multiplication -------------------------------------------------- */
+/* out = sum_i scalars[i] * bases[offset + i], i < n.  Replaces gnark-crypto
+ * ecc/bn254 (*G1Affine).MultiExp / (*G2Affine).MultiExp as called by gnark
+ * backend/groth16/bn254/prove.go (Ar, Bs1, Krs, Krs2/Z, Bs2) and by
+ * fr/pedersen ProvingKey.Commit / ProveKnowledge (the BSB22 commitment, inside Solve).
+ * scalars: n fr.Element (Montgomery) in HOST memory. */
+int b200g16_msm_g1(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                   const uint64_t* scalars, size_t n, uint64_t out_affine[8]);
+int b200g16_msm_g2(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                   const uint64_t* scalars, size_t n, uint64_t out_affine[16]);
+/* Same, scalars already resident in DEVICE memory (the prover feeds h straight from
+ * computeH; bench.py's device-resident throughput leg). */
+int b200g16_msm_g1_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                       const void* d_scalars, size_t n, uint64_t out_affine[8]);
+int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                       const void* d_scalars, size_t n, uint64_t out_affine[16]);
+
+/* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
+/* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
+int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);
+int b200g16_g2_add(const uint64_t a[16], const uint64_t b[16], uint64_t out[16]);
+/* out = k * p, k an fr.Element in Montgomery form (gnark ScalarMultiplication). Host only. */
+int b200g16_g1_scalar_mul(const uint64_t p[8], const uint64_t k[4], uint64_t out[8]);
+int b200g16_g2_scalar_mul(const uint64_t p[16], const uint64_t k[4], uint64_t out[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200G16_H */
