@@ -10,6 +10,13 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, 
 template <class F>
 int fixed_base_mul_device(b200g16_ctx* ctx, const Affine<F>& base, const Fr* d_scalars, size_t n, Affine<F>* d_out);
 int modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, double* modmul_per_s, float* ms_out);
+int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation);
+int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L);
+int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n);
+int sponge_batch_device(b200g16_ctx* ctx, const uint8_t* d_in, size_t in_len, size_t n, uint8_t* d_out, size_t out_len);
+int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_len, const uint64_t* d_sib,
+                        const uint64_t* d_auth, const uint64_t* d_idx, unsigned height, size_t n,
+                        const uint64_t* d_expected_root, uint64_t* d_roots, uint8_t* d_ok);
 
 // out[i] = k_i * base; result either copied to the host (out_host) or kept as a new bases handle
 template <class F>
@@ -154,7 +161,7 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->msm.counts, &ctx->msm.partials,
                     &ctx->msm.buckets, &ctx->msm.chunks,  &ctx->msm.windows, &ctx->msm.misc,   &ctx->msm.tasks,
-                    &ctx->ntt.a,       &ctx->ntt.b,       &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->io_a,
+                    &ctx->ntt.a,       &ctx->ntt.b,       &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->io_a,
                     &ctx->io_b,        &ctx->io_c};
   for (DevBuf* b : bufs) b->release();
   if (ctx->msm.pinned) cudaFreeHost(ctx->msm.pinned);
@@ -241,6 +248,148 @@ int b200g16_msm_g1_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offs
 int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const void* d_scalars, size_t n,
                        uint64_t out[16]) {
   return msm_entry<Fp2>(ctx, bases, 2, offset, d_scalars, true, n, out);
+}
+
+int b200g16_ntt_dev(b200g16_ctx* ctx, void* d_data, unsigned log2n, unsigned batch, int inverse, int coset,
+                    int decimation) {
+  if (!ctx || !d_data) return fail(B200G16_ERR_ARG, "ntt: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(ntt_device(ctx, reinterpret_cast<Fr*>(d_data), (int)log2n, (int)batch, inverse != 0, coset != 0, decimation));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_ntt(b200g16_ctx* ctx, uint64_t* data, unsigned log2n, int inverse, int coset, int decimation) {
+  if (!ctx || !data) return fail(B200G16_ERR_ARG, "ntt: null");
+  if (log2n > 28) return fail(B200G16_ERR_ARG, "ntt: log2n=%u exceeds the field's two-adicity (28)", log2n);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  size_t bytes = ((size_t)1 << log2n) * sizeof(Fr);
+  B200_TRY(ctx->ntt.a.ensure(bytes));
+  B200_CUDA(cudaMemcpyAsync(ctx->ntt.a.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(ntt_device(ctx, ctx->ntt.a.as<Fr>(), (int)log2n, 1, inverse != 0, coset != 0, decimation));
+  B200_CUDA(cudaMemcpyAsync(data, ctx->ntt.a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_compute_h_dev(b200g16_ctx* ctx, void* d_a, void* d_b, void* d_c, unsigned log2n) {
+  if (!ctx || !d_a || !d_b || !d_c) return fail(B200G16_ERR_ARG, "compute_h: null");
+  if (log2n > 28) return fail(B200G16_ERR_ARG, "compute_h: log2n=%u exceeds two-adicity 28", log2n);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return compute_h_device(ctx, reinterpret_cast<Fr*>(d_a), reinterpret_cast<Fr*>(d_b), reinterpret_cast<Fr*>(d_c),
+                          (int)log2n);
+}
+
+int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
+                      unsigned log2n, uint64_t* h_out) {
+  if (!ctx || !a || !b || !c || !h_out) return fail(B200G16_ERR_ARG, "compute_h: null");
+  if (log2n > 28) return fail(B200G16_ERR_ARG, "compute_h: log2n=%u exceeds two-adicity 28", log2n);
+  size_t n = (size_t)1 << log2n;
+  if (n_constraints > n) return fail(B200G16_ERR_ARG, "compute_h: %zu constraints > domain %zu", n_constraints, n);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  DevBuf* bufs[3] = {&ctx->ntt.a, &ctx->ntt.b, &ctx->ntt.c};
+  const uint64_t* src[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    B200_TRY(bufs[i]->ensure(n * sizeof(Fr)));
+    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > n_constraints)  // computeH pads a, b, c with zeros up to the domain cardinality
+      B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (n - n_constraints) * sizeof(Fr),
+                                ctx->stream));
+  }
+  B200_TRY(compute_h_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), (int)log2n));
+  B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, n * sizeof(Fr), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200g16_keccak_f_batch_dev(b200g16_ctx* ctx, void* d_states, size_t n) {
+  if (!ctx || (n && !d_states)) return fail(B200G16_ERR_ARG, "keccak_f_batch: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(keccak_f_batch_device(ctx, reinterpret_cast<uint64_t*>(d_states), n));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_keccak_f_batch(b200g16_ctx* ctx, uint64_t* states, size_t n) {
+  if (!ctx || (n && !states)) return fail(B200G16_ERR_ARG, "keccak_f_batch: null");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  size_t bytes = n * 200;
+  B200_TRY(ctx->io_a.ensure(bytes));
+  B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(keccak_f_batch_device(ctx, ctx->io_a.as<uint64_t>(), n));
+  B200_CUDA(cudaMemcpyAsync(states, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_keccak_sponge_batch(b200g16_ctx* ctx, const uint8_t* inputs, size_t in_len, size_t n, uint8_t* outputs,
+                                size_t out_len) {
+  if (!ctx || (n && in_len && !inputs) || (n && out_len && !outputs)) return fail(B200G16_ERR_ARG, "sponge: null");
+  if (n == 0 || out_len == 0) return 0;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(ctx->io_a.ensure(n * in_len + 8));
+  B200_TRY(ctx->io_b.ensure(n * out_len));
+  if (in_len) B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, inputs, n * in_len, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(sponge_batch_device(ctx, ctx->io_a.as<uint8_t>(), in_len, n, ctx->io_b.as<uint8_t>(), out_len));
+  B200_CUDA(cudaMemcpyAsync(outputs, ctx->io_b.p, n * out_len, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_keccak_merkle_paths_dev(b200g16_ctx* ctx, const void* d_leaves, size_t leaf_len, const void* d_siblings,
+                                    const void* d_auth_paths, const void* d_indexes, unsigned height, size_t n_paths,
+                                    const void* d_expected_root, void* d_roots_out, void* d_ok_out) {
+  if (!ctx) return fail(B200G16_ERR_ARG, "merkle: null ctx");
+  if (height < 1 || height > 64) return fail(B200G16_ERR_ARG, "merkle: height %u", height);
+  if (leaf_len == 0 || leaf_len % 8) return fail(B200G16_ERR_ARG, "merkle: leaf_len must be a positive multiple of 8");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(merkle_paths_device(ctx, (const uint8_t*)d_leaves, leaf_len, (const uint64_t*)d_siblings,
+                               (const uint64_t*)d_auth_paths, (const uint64_t*)d_indexes, height, n_paths,
+                               (const uint64_t*)d_expected_root, (uint64_t*)d_roots_out, (uint8_t*)d_ok_out));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_keccak_merkle_paths(b200g16_ctx* ctx, const uint8_t* leaves, size_t leaf_len, const uint8_t* siblings,
+                                const uint8_t* auth_paths, const uint64_t* indexes, unsigned height, size_t n_paths,
+                                const uint8_t* expected_root, uint8_t* roots_out, uint8_t* ok_out) {
+  if (!ctx || !leaves || !siblings || !indexes || (height > 1 && !auth_paths) || (!roots_out && !ok_out))
+    return fail(B200G16_ERR_ARG, "merkle: null");
+  if (height < 1 || height > 64) return fail(B200G16_ERR_ARG, "merkle: height %u", height);
+  if (leaf_len == 0 || leaf_len % 8) return fail(B200G16_ERR_ARG, "merkle: leaf_len must be a positive multiple of 8");
+  if (ok_out && !expected_root) return fail(B200G16_ERR_ARG, "merkle: ok_out needs expected_root");
+  if (n_paths == 0) return 0;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = n_paths;
+  const size_t sz_leaves = n * leaf_len, sz_sib = n * 32, sz_auth = n * (size_t)(height - 1) * 32, sz_idx = n * 8;
+  auto up8 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t o_sib = up8(sz_leaves), o_auth = o_sib + up8(sz_sib), o_idx = o_auth + up8(sz_auth),
+         o_root = o_idx + up8(sz_idx), o_roots = o_root + 32, o_ok = o_roots + up8(n * 32), total = o_ok + up8(n);
+  B200_TRY(ctx->io_a.ensure(total));
+  char* d = ctx->io_a.as<char>();
+  cudaStream_t st = ctx->stream;
+  B200_CUDA(cudaMemcpyAsync(d, leaves, sz_leaves, cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(d + o_sib, siblings, sz_sib, cudaMemcpyHostToDevice, st));
+  if (sz_auth) B200_CUDA(cudaMemcpyAsync(d + o_auth, auth_paths, sz_auth, cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(d + o_idx, indexes, sz_idx, cudaMemcpyHostToDevice, st));
+  if (expected_root) B200_CUDA(cudaMemcpyAsync(d + o_root, expected_root, 32, cudaMemcpyHostToDevice, st));
+  B200_TRY(merkle_paths_device(ctx, (const uint8_t*)d, leaf_len, (const uint64_t*)(d + o_sib),
+                               (const uint64_t*)(d + o_auth), (const uint64_t*)(d + o_idx), height, n,
+                               expected_root ? (const uint64_t*)(d + o_root) : nullptr, (uint64_t*)(d + o_roots),
+                               ok_out ? (uint8_t*)(d + o_ok) : nullptr));
+  if (roots_out) B200_CUDA(cudaMemcpyAsync(roots_out, d + o_roots, n * 32, cudaMemcpyDeviceToHost, st));
+  if (ok_out) B200_CUDA(cudaMemcpyAsync(ok_out, d + o_ok, n, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]) {

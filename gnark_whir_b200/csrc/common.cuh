@@ -71,8 +71,9 @@ struct MsmWorkspace {
 };
 
 struct NttWorkspace {
-  DevBuf a, b, c, tw;
-  int tw_log = -1;
+  DevBuf a, b, c, tw, coset;
+  int tw_log = -1;     // twiddle table covers 2^tw_log
+  int coset_log = -1;  // coset tables built for exactly 2^coset_log
 };
 
 struct Timings {

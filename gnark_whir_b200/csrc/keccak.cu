@@ -1,0 +1,255 @@
+// Batched Keccak-f[1600], the reference's overwrite-mode duplex sponge, and Merkle-path
+// recomputation, for sm_100a.
+//
+//   k_keccak_f_batch  <- gnark std/permutation/keccakf.Permute as called at
+//                        /root/reference/keccakSponge/keccakSponge.go:48,69 (FIPS-202 permutation
+//                        on 25 little-endian u64 lanes, lane index x + 5y)
+//   k_sponge_batch    <- keccakSponge.Digest: NewKeccak / Absorb / Squeeze
+//                        (keccakSponge.go:17-30, 40-56, 64-75): rate 136 B, OVERWRITE absorb,
+//                        no padding, permute-on-full and permute-before-first-squeeze
+//   k_merkle_paths    <- VerifyMerkleTreeProofs (/root/reference/mtUtilities.go:109-141): leaf hash,
+//                        then per level pair with the sibling by the index bit (bit 0 uses
+//                        LeafSiblingHashes, bit k>=1 uses AuthPaths[k-1]; set bit => current node
+//                        is the right child), compare with the root.  The 2-to-1 hash is the
+//                        Keccak duplex above, as BASELINE.json config 4 specifies.
+//
+// One thread owns one state: 25 lanes = 50 registers, 24 fully unrolled rounds; chi is a
+// single LOP3 per 32-bit half and theta's 5-way XOR two LOP3s, so the kernel is LOP3/SHF
+// (ALU-pipe) bound, not HBM bound (400 B of traffic per ~3.7k 64-bit logic ops).
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int KECCAK_RATE = 136;
+constexpr int KECCAK_RATE_LANES = 17;
+
+__constant__ uint64_t kRC[24] = {
+    0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+    0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+    0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+    0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+    0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+
+__device__ __forceinline__ uint64_t rol64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
+
+__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
+#pragma unroll
+  for (int rnd = 0; rnd < 24; rnd++) {
+    uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20];
+    uint64_t c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21];
+    uint64_t c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22];
+    uint64_t c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23];
+    uint64_t c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
+    uint64_t d0 = c4 ^ rol64(c1, 1);
+    uint64_t d1 = c0 ^ rol64(c2, 1);
+    uint64_t d2 = c1 ^ rol64(c3, 1);
+    uint64_t d3 = c2 ^ rol64(c4, 1);
+    uint64_t d4 = c3 ^ rol64(c0, 1);
+    // theta + rho + pi:  b[y + 5((2x+3y)%5)] = rol(a[x+5y] ^ d[x], ROT[x][y])
+    uint64_t b0 = a[0] ^ d0;
+    uint64_t b10 = rol64(a[1] ^ d1, 1);
+    uint64_t b20 = rol64(a[2] ^ d2, 62);
+    uint64_t b5 = rol64(a[3] ^ d3, 28);
+    uint64_t b15 = rol64(a[4] ^ d4, 27);
+    uint64_t b16 = rol64(a[5] ^ d0, 36);
+    uint64_t b1 = rol64(a[6] ^ d1, 44);
+    uint64_t b11 = rol64(a[7] ^ d2, 6);
+    uint64_t b21 = rol64(a[8] ^ d3, 55);
+    uint64_t b6 = rol64(a[9] ^ d4, 20);
+    uint64_t b7 = rol64(a[10] ^ d0, 3);
+    uint64_t b17 = rol64(a[11] ^ d1, 10);
+    uint64_t b2 = rol64(a[12] ^ d2, 43);
+    uint64_t b12 = rol64(a[13] ^ d3, 25);
+    uint64_t b22 = rol64(a[14] ^ d4, 39);
+    uint64_t b23 = rol64(a[15] ^ d0, 41);
+    uint64_t b8 = rol64(a[16] ^ d1, 45);
+    uint64_t b18 = rol64(a[17] ^ d2, 15);
+    uint64_t b3 = rol64(a[18] ^ d3, 21);
+    uint64_t b13 = rol64(a[19] ^ d4, 8);
+    uint64_t b14 = rol64(a[20] ^ d0, 18);
+    uint64_t b24 = rol64(a[21] ^ d1, 2);
+    uint64_t b9 = rol64(a[22] ^ d2, 61);
+    uint64_t b19 = rol64(a[23] ^ d3, 56);
+    uint64_t b4 = rol64(a[24] ^ d4, 14);
+    // chi
+    a[0] = b0 ^ (~b1 & b2);   a[1] = b1 ^ (~b2 & b3);   a[2] = b2 ^ (~b3 & b4);
+    a[3] = b3 ^ (~b4 & b0);   a[4] = b4 ^ (~b0 & b1);
+    a[5] = b5 ^ (~b6 & b7);   a[6] = b6 ^ (~b7 & b8);   a[7] = b7 ^ (~b8 & b9);
+    a[8] = b8 ^ (~b9 & b5);   a[9] = b9 ^ (~b5 & b6);
+    a[10] = b10 ^ (~b11 & b12); a[11] = b11 ^ (~b12 & b13); a[12] = b12 ^ (~b13 & b14);
+    a[13] = b13 ^ (~b14 & b10); a[14] = b14 ^ (~b10 & b11);
+    a[15] = b15 ^ (~b16 & b17); a[16] = b16 ^ (~b17 & b18); a[17] = b17 ^ (~b18 & b19);
+    a[18] = b18 ^ (~b19 & b15); a[19] = b19 ^ (~b15 & b16);
+    a[20] = b20 ^ (~b21 & b22); a[21] = b21 ^ (~b22 & b23); a[22] = b22 ^ (~b23 & b24);
+    a[23] = b23 ^ (~b24 & b20); a[24] = b24 ^ (~b20 & b21);
+    // iota
+    a[0] ^= kRC[rnd];
+  }
+}
+
+// ---- raw batch: states[i][25] permuted in place.  A warp stages its 32 states (6400
+// contiguous bytes) through shared memory so the global accesses are fully coalesced.
+constexpr int KF_THREADS = 128;
+__global__ void __launch_bounds__(KF_THREADS) k_keccak_f_batch(uint64_t* __restrict__ states, size_t n) {
+  __shared__ uint64_t sm[KF_THREADS / 32][32 * 25];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t warp_first = ((size_t)blockIdx.x * KF_THREADS + (size_t)warp * 32);
+  if (warp_first >= n) return;
+  const size_t in_warp = n - warp_first < 32 ? n - warp_first : 32;
+  uint64_t* g = states + warp_first * 25;
+  const uint32_t words = (uint32_t)in_warp * 25;
+#pragma unroll
+  for (int j = 0; j < 25; j++) {
+    uint32_t w = lane + 32 * j;
+    if (w < words) sm[warp][w] = g[w];
+  }
+  __syncwarp();
+  uint64_t a[25];
+  if (lane < in_warp) {
+#pragma unroll
+    for (int l = 0; l < 25; l++) a[l] = sm[warp][lane * 25 + l];
+    keccak_f1600(a);
+#pragma unroll
+    for (int l = 0; l < 25; l++) sm[warp][lane * 25 + l] = a[l];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 25; j++) {
+    uint32_t w = lane + 32 * j;
+    if (w < words) g[w] = sm[warp][w];
+  }
+}
+
+// ---- sponge helpers.  `len` bytes at `src` overwrite the first bytes of the rate, block by block.
+__device__ __forceinline__ uint64_t load_le64_partial(const uint8_t* p, int nbytes) {
+  uint64_t v = 0;
+  for (int k = 0; k < nbytes; k++) v |= (uint64_t)p[k] << (8 * k);
+  return v;
+}
+
+// absorb `len` bytes then permute once more (the permute Squeeze issues first): state after
+// NewKeccak(); Absorb(src[:len]); and the permutation at the head of Squeeze.
+template <bool ALIGNED8>
+__device__ __forceinline__ void sponge_absorb_finish(uint64_t (&a)[25], const uint8_t* src, size_t len) {
+  size_t off = 0;
+  while (len - off > KECCAK_RATE) {  // full blocks followed by more data: overwrite + permute
+#pragma unroll
+    for (int l = 0; l < KECCAK_RATE_LANES; l++)
+      a[l] = ALIGNED8 ? reinterpret_cast<const uint64_t*>(src + off)[l] : load_le64_partial(src + off + 8 * l, 8);
+    keccak_f1600(a);
+    off += KECCAK_RATE;
+  }
+  int rem = (int)(len - off);  // 0..136 bytes in the last block (0 only when len == 0)
+#pragma unroll
+  for (int l = 0; l < KECCAK_RATE_LANES; l++) {
+    int nb = rem - 8 * l;
+    if (nb >= 8) {
+      a[l] = ALIGNED8 ? reinterpret_cast<const uint64_t*>(src + off)[l] : load_le64_partial(src + off + 8 * l, 8);
+    } else if (nb > 0) {
+      uint64_t mask = (1ull << (8 * nb)) - 1;
+      a[l] = (a[l] & ~mask) | load_le64_partial(src + off + 8 * l, nb);
+    }
+  }
+  keccak_f1600(a);
+}
+
+// squeeze out_len bytes (state already permuted once)
+__device__ __forceinline__ void sponge_squeeze(uint64_t (&a)[25], uint8_t* dst, size_t out_len) {
+  size_t done = 0;
+  while (true) {
+    size_t take = out_len - done < KECCAK_RATE ? out_len - done : KECCAK_RATE;
+#pragma unroll
+    for (int l = 0; l < KECCAK_RATE_LANES; l++) {
+      long nb = (long)take - 8 * l;
+      if (nb > 0) {
+        uint64_t v = a[l];
+        for (int k = 0; k < (nb < 8 ? nb : 8); k++) dst[done + 8 * l + k] = (uint8_t)(v >> (8 * k));
+      }
+    }
+    done += take;
+    if (done >= out_len) break;
+    keccak_f1600(a);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sponge_batch(const uint8_t* __restrict__ in, size_t in_len, size_t n,
+                                                       uint8_t* __restrict__ out, size_t out_len, int aligned8) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t a[25];
+#pragma unroll
+  for (int l = 0; l < 25; l++) a[l] = 0;
+  if (aligned8) sponge_absorb_finish<true>(a, in + i * in_len, in_len);
+  else sponge_absorb_finish<false>(a, in + i * in_len, in_len);
+  sponge_squeeze(a, out + i * out_len, out_len);
+}
+
+// ---- Merkle paths.  Digests are 32 bytes = lanes 0..3 of the squeezed state.
+__global__ void __launch_bounds__(128) k_merkle_paths(const uint8_t* __restrict__ leaves, size_t leaf_len,
+                                                       const uint64_t* __restrict__ leaf_siblings,
+                                                       const uint64_t* __restrict__ auth_paths,
+                                                       const uint64_t* __restrict__ indexes, unsigned height,
+                                                       size_t n, const uint64_t* __restrict__ expected_root,
+                                                       uint64_t* __restrict__ roots_out, uint8_t* __restrict__ ok_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t a[25];
+#pragma unroll
+  for (int l = 0; l < 25; l++) a[l] = 0;
+  sponge_absorb_finish<true>(a, leaves + i * leaf_len, leaf_len);
+  uint64_t cur[4] = {a[0], a[1], a[2], a[3]};
+  const uint64_t idx = indexes[i];
+  const uint64_t* ap = auth_paths + i * (size_t)(height - 1) * 4;
+  for (unsigned level = 0; level < height; level++) {
+    const uint64_t* sp = level == 0 ? leaf_siblings + i * 4 : ap + (size_t)(level - 1) * 4;
+    uint64_t s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+    bool right = (idx >> level) & 1;  // set bit: current node is the right child
+#pragma unroll
+    for (int l = 8; l < 25; l++) a[l] = 0;
+    a[0] = right ? s0 : cur[0]; a[1] = right ? s1 : cur[1]; a[2] = right ? s2 : cur[2]; a[3] = right ? s3 : cur[3];
+    a[4] = right ? cur[0] : s0; a[5] = right ? cur[1] : s1; a[6] = right ? cur[2] : s2; a[7] = right ? cur[3] : s3;
+    keccak_f1600(a);
+    cur[0] = a[0]; cur[1] = a[1]; cur[2] = a[2]; cur[3] = a[3];
+  }
+  if (roots_out) {
+    roots_out[i * 4 + 0] = cur[0]; roots_out[i * 4 + 1] = cur[1];
+    roots_out[i * 4 + 2] = cur[2]; roots_out[i * 4 + 3] = cur[3];
+  }
+  if (ok_out)
+    ok_out[i] = expected_root && cur[0] == expected_root[0] && cur[1] == expected_root[1] &&
+                cur[2] == expected_root[2] && cur[3] == expected_root[3];
+}
+
+// ------------------------------------------------------------------------------ host drivers
+int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n) {
+  if (n == 0) return 0;
+  unsigned grid = (unsigned)((n + KF_THREADS - 1) / KF_THREADS);
+  k_keccak_f_batch<<<grid, KF_THREADS, 0, ctx->stream>>>(d_states, n);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sponge_batch_device(b200g16_ctx* ctx, const uint8_t* d_in, size_t in_len, size_t n, uint8_t* d_out,
+                        size_t out_len) {
+  if (n == 0) return 0;
+  int aligned8 = (in_len % 8 == 0) && (((uintptr_t)d_in) % 8 == 0);
+  k_sponge_batch<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_in, in_len, n, d_out, out_len, aligned8);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_len, const uint64_t* d_sib,
+                        const uint64_t* d_auth, const uint64_t* d_idx, unsigned height, size_t n,
+                        const uint64_t* d_expected_root, uint64_t* d_roots, uint8_t* d_ok) {
+  if (n == 0) return 0;
+  k_merkle_paths<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_leaves, leaf_len, d_sib, d_auth, d_idx,
+                                                                        height, n, d_expected_root, d_roots, d_ok);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,363 @@
+// Fr number-theoretic transforms with gnark-crypto's fft.Domain conventions, and groth16's
+// computeH, for sm_100a.
+//
+// Replaces gnark-crypto ecc/bn254/fr/fft (Domain.FFT / Domain.FFTInverse with fft.DIF /
+// fft.DIT / fft.OnCoset()) and gnark backend/groth16/bn254/prove.go computeH, reached from
+// the reference at /root/reference/mt.go:496 (the Domain itself is built by Setup, mt.go:448).
+//
+//   DIF: natural-order input -> bit-reversed output (Gentleman-Sande butterflies)
+//   DIT: bit-reversed input -> natural-order output (Cooley-Tukey butterflies)
+//   OnCoset: forward multiplies a[i] by g^i first (index bit-reversed when DIT); inverse
+//            multiplies by g^-i/N last (index bit-reversed when DIF); g = 5.
+//
+// Kernel structure: log2 N levels are split into passes of <= 8 levels.  A pass owns the index
+// bits [b0, b0+k): a CTA loads a tile of 2^k "rows" x 8 contiguous "columns" (256 B chunks,
+// coalesced) into shared memory, runs the k radix-2 levels there (split lo/hi uint4 layout so
+// consecutive lanes hit consecutive banks), and stores the tile back: 64 B of HBM traffic per
+// element per pass.  Coset / 1/N scaling rides on the first pass's load or the last pass's
+// store.  Twiddles come from one table w^e (e < N/2): the pass over the top bits streams it
+// once, later passes reuse a few KB of it out of L1/L2; inverse transforms read the same table
+// through w^-e = -w^(N/2-e).
+#include "common.cuh"
+#include "field.cuh"
+
+namespace b200 {
+
+constexpr int NTT_MAX_K = 8;
+constexpr int NTT_LOGC = 3;
+constexpr int NTT_THREADS = 256;
+
+static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+__device__ __forceinline__ uint32_t bitrev_dev(uint32_t i, int L) { return __brev(i) >> (32 - L); }
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+  Fr r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4 a = s[0], b = s[1];
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+  Fr r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(s), b = __ldg(s + 1);
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+  d[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  d[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+struct SmemTile {
+  uint4* lo;
+  uint4* hi;
+  __device__ __forceinline__ Fr get(uint32_t s) const {
+    uint4 a = lo[s], b = hi[s];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ void put(uint32_t s, const Fr& v) const {
+    lo[s] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[s] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  }
+};
+
+// w^e (or w^-e) from the forward table; `half` = N_table/2, sh = log2(N_table/N)
+__device__ __forceinline__ Fr twiddle(const Fr* __restrict__ tw, uint32_t e, int sh, uint32_t half, bool inverse) {
+  uint32_t idx = e << sh;
+  if (!inverse || idx == 0) return ldg_fr(tw + idx);
+  return Fr::neg(ldg_fr(tw + (half - idx)));
+}
+
+struct NttPassArgs {
+  Fr* data;
+  const Fr* tw;
+  const Fr* pre;    // multiply on load by pre[idx]  (nullptr = none)
+  const Fr* post;   // multiply on store by post[idx] (nullptr = none)
+  Fr post_const;    // used when post_mode == 1
+  uint32_t tw_half;
+  int tw_sh;
+  int L, b0, k, logc;
+  int post_mode;    // 0 none, 1 const, 2 table
+  int pre_bitrev, post_bitrev;
+  int inverse;
+};
+
+// TFAST: rows contiguous in memory (b0 == 0) -> row index fastest in shared memory.
+template <bool DIT, bool TFAST>
+__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = A.k, L = A.L, b0 = A.b0, logc = A.logc;
+  const uint32_t rows = 1u << k;
+  const uint32_t T = rows << logc;  // elements per tile
+  SmemTile sm{reinterpret_cast<uint4*>(smem_raw), reinterpret_cast<uint4*>(smem_raw) + T};
+  const uint32_t lowmask = (1u << b0) - 1u;
+  const uint32_t tile = blockIdx.x;
+  Fr* data = A.data + (size_t)blockIdx.y * ((size_t)1 << L);  // batched transforms
+
+  // ---- load
+  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+    uint32_t t, c;
+    if (TFAST) { t = x & (rows - 1); c = x >> k; }
+    else { c = x & ((1u << logc) - 1); t = x >> logc; }
+    uint32_t u = (tile << logc) + c;
+    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
+    Fr v = ld_fr(data + i);
+    if (A.pre) v = Fr::mul(v, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i, L) : i)));
+    sm.put(x, v);  // x is exactly the shared-memory slot for this layout
+  }
+  __syncthreads();
+
+  // ---- k radix-2 levels
+  const uint32_t nbf = T >> 1;
+  for (int step = 0; step < k; step++) {
+    const int lb = DIT ? step : (k - 1 - step);  // local partner bit
+    const int pb = b0 + lb;                      // global partner bit
+    const uint32_t lbmask = (1u << lb) - 1u;
+    for (uint32_t q = threadIdx.x; q < nbf; q += NTT_THREADS) {
+      uint32_t r, c;
+      if (TFAST) { r = q & ((rows >> 1) - 1); c = q >> (k - 1); }
+      else { c = q & ((1u << logc) - 1); r = q >> logc; }
+      uint32_t t0 = ((r >> lb) << (lb + 1)) | (r & lbmask);
+      uint32_t t1 = t0 | (1u << lb);
+      uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
+      uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
+      uint32_t u = (tile << logc) + c;
+      uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
+      uint32_t e = j << (L - 1 - pb);
+      Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
+      Fr xv = sm.get(s0), yv = sm.get(s1);
+      if (DIT) {
+        yv = Fr::mul(yv, w);
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::sub(xv, yv));
+      } else {
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::mul(Fr::sub(xv, yv), w));
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- store
+  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+    uint32_t t, c;
+    if (TFAST) { t = x & (rows - 1); c = x >> k; }
+    else { c = x & ((1u << logc) - 1); t = x >> logc; }
+    uint32_t u = (tile << logc) + c;
+    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
+    Fr v = sm.get(x);
+    if (A.post_mode == 1) v = Fr::mul(v, A.post_const);
+    else if (A.post_mode == 2) v = Fr::mul(v, ldg_fr(A.post + (A.post_bitrev ? bitrev_dev(i, L) : i)));
+    st_fr(data + i, v);
+  }
+}
+
+// t[s + i] = t[i] * step  for i < s   (doubling construction of geometric tables)
+__global__ void __launch_bounds__(256) k_geom_expand(Fr* __restrict__ t, uint32_t s, uint32_t limit, Fr step) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s || s + i >= limit) return;
+  st_fr(t + s + i, Fr::mul(ld_fr(t + i), step));
+}
+
+// a[i] = (a[i] * b[i] - c[i]) * den
+__global__ void __launch_bounds__(256) k_h_pointwise(Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                      const Fr* __restrict__ c, uint32_t n, Fr den) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr v = Fr::sub(Fr::mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i));
+  st_fr(a + i, Fr::mul(v, den));
+}
+
+// ------------------------------------------------------------------------------ host side
+static Fr fr_from_limbs(const uint32_t (&l)[8]) {
+  Fr r;
+  for (int i = 0; i < 8; i++) r.l[i] = l[i];
+  return r;
+}
+static Fr fr_pow_u64(Fr a, uint64_t e) {
+  Fr r = Fr::one();
+  while (e) {
+    if (e & 1) r = Fr::mul(r, a);
+    a = Fr::sqr(a);
+    e >>= 1;
+  }
+  return r;
+}
+static Fr fr_from_u64(uint64_t v) {
+  Fr r = Fr::zero();
+  r.l[0] = (uint32_t)v;
+  r.l[1] = (uint32_t)(v >> 32);
+  return Fr::to_mont(r);
+}
+
+// Build t[0..count) = first * ratio^i on the device.
+static int build_geometric(b200g16_ctx* ctx, Fr* d_t, size_t count, const Fr& first, Fr ratio) {
+  B200_CUDA(cudaMemcpyAsync(d_t, &first, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));  // `first` is a host temporary
+  Fr step = ratio;                                // ratio^s
+  for (size_t s = 1; s < count; s <<= 1) {
+    k_geom_expand<<<cdiv_u(s, 256), 256, 0, ctx->stream>>>(d_t, (uint32_t)s, (uint32_t)count, step);
+    ctx->launches++;
+    step = Fr::sqr(step);
+  }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+struct NttDomain {
+  int L = -1;
+  Fr w, w_inv, n_inv;
+};
+
+static void domain_params(int L, NttDomain* d) {
+  const uint32_t root[8] = B200_FR_ROOT28;
+  const uint32_t root_inv[8] = B200_FR_ROOT28_INV;
+  Fr w = fr_from_limbs(root), wi = fr_from_limbs(root_inv);
+  for (int i = L; i < 28; i++) { w = Fr::sqr(w); wi = Fr::sqr(wi); }
+  d->L = L;
+  d->w = w;
+  d->w_inv = wi;
+  d->n_inv = Fr::inv(fr_from_u64(1ull << L));
+}
+
+// twiddle table w^e, e < N/2, for the largest N seen so far
+static int ensure_twiddles(b200g16_ctx* ctx, int L) {
+  NttWorkspace& ws = ctx->ntt;
+  if (ws.tw_log >= L) return 0;
+  size_t half = (size_t)1 << (L > 0 ? L - 1 : 0);
+  B200_TRY(ws.tw.ensure(half * sizeof(Fr)));
+  NttDomain d;
+  domain_params(L, &d);
+  B200_TRY(build_geometric(ctx, ws.tw.as<Fr>(), half, Fr::one(), d.w));
+  ws.tw_log = L;
+  return 0;
+}
+
+// coset tables for size 2^L: fwd[i] = g^i, inv[i] = g^-i / N
+static int ensure_coset(b200g16_ctx* ctx, int L) {
+  NttWorkspace& ws = ctx->ntt;
+  if (ws.coset_log == L) return 0;
+  size_t n = (size_t)1 << L;
+  B200_TRY(ws.coset.ensure(2 * n * sizeof(Fr)));
+  const uint32_t g[8] = B200_FR_GEN;
+  const uint32_t gi[8] = B200_FR_GEN_INV;
+  NttDomain d;
+  domain_params(L, &d);
+  B200_TRY(build_geometric(ctx, ws.coset.as<Fr>(), n, Fr::one(), fr_from_limbs(g)));
+  B200_TRY(build_geometric(ctx, ws.coset.as<Fr>() + n, n, d.n_inv, fr_from_limbs(gi)));
+  ws.coset_log = L;
+  return 0;
+}
+
+// In-place transform of `batch` consecutive vectors of 2^L elements at d_data.
+int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation) {
+  if (L < 0 || L > 28) return fail(B200G16_ERR_ARG, "ntt: log2n=%d out of range (two-adicity 28)", L);
+  if (decimation != B200G16_DIF && decimation != B200G16_DIT) return fail(B200G16_ERR_ARG, "ntt: bad decimation");
+  if (batch < 1) return fail(B200G16_ERR_ARG, "ntt: batch");
+  B200_TRY(ensure_twiddles(ctx, L));
+  if (coset) B200_TRY(ensure_coset(ctx, L));
+  NttWorkspace& ws = ctx->ntt;
+  const size_t n = (size_t)1 << L;
+  const bool dit = decimation == B200G16_DIT;
+  NttDomain dom;
+  domain_params(L, &dom);
+
+  NttPassArgs A;
+  A.data = d_data;
+  A.tw = ws.tw.as<Fr>();
+  A.tw_sh = ws.tw_log - L;
+  A.tw_half = (uint32_t)(((size_t)1 << ws.tw_log) >> 1);
+  A.L = L;
+  A.inverse = inverse ? 1 : 0;
+  A.post_const = dom.n_inv;
+
+  // forward-coset scaling on the first load, inverse scaling on the last store
+  const Fr* pre = (coset && !inverse) ? ws.coset.as<Fr>() : nullptr;
+  const int pre_bitrev = dit ? 1 : 0;        // DIT input is bit-reversed
+  int post_mode = 0;
+  const Fr* post = nullptr;
+  if (inverse) {
+    if (coset) { post_mode = 2; post = ws.coset.as<Fr>() + n; }
+    else post_mode = 1;
+  }
+  const int post_bitrev = dit ? 0 : 1;       // DIF output is bit-reversed
+
+  if (L == 0) {  // single element: only scaling applies (n_inv = 1, g^0 = 1) -> nothing to do
+    return 0;
+  }
+  // split L levels into passes of <= NTT_MAX_K, as evenly as possible
+  int npass = (L + NTT_MAX_K - 1) / NTT_MAX_K;
+  int ks[8];
+  for (int p = 0; p < npass; p++) ks[p] = L / npass + (p < L % npass ? 1 : 0);
+  // DIF walks partner bits from the top down, DIT from the bottom up
+  int b0s[8];
+  if (dit) { int b = 0; for (int p = 0; p < npass; p++) { b0s[p] = b; b += ks[p]; } }
+  else { int b = L; for (int p = 0; p < npass; p++) { b -= ks[p]; b0s[p] = b; } }
+
+  for (int p = 0; p < npass; p++) {
+    A.k = ks[p];
+    A.b0 = b0s[p];
+    A.pre = (p == 0) ? pre : nullptr;
+    A.pre_bitrev = pre_bitrev;
+    A.post_mode = (p == npass - 1) ? post_mode : 0;
+    A.post = post;
+    A.post_bitrev = post_bitrev;
+    // tile = 2^k rows x 2^logc columns (8 columns = 256 B chunks unless the vector is tiny)
+    int logc = L - A.k < NTT_LOGC ? L - A.k : NTT_LOGC;
+    A.logc = logc;
+    size_t tiles = n >> (A.k + logc);
+    size_t smem = ((size_t)1 << (A.k + logc)) * sizeof(Fr);
+    dim3 grid((unsigned)tiles, (unsigned)batch);
+    bool tfast = (A.b0 == 0);
+#define B200_LAUNCH_PASS(DITV, TF)                                                                          \
+    do {                                                                                                     \
+      B200_CUDA(cudaFuncSetAttribute(k_ntt_pass<DITV, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)(((size_t)1 << (NTT_MAX_K + NTT_LOGC)) * sizeof(Fr))));            \
+      k_ntt_pass<DITV, TF><<<grid, NTT_THREADS, smem, ctx->stream>>>(A);                                     \
+    } while (0)
+    if (dit) { if (tfast) B200_LAUNCH_PASS(true, true); else B200_LAUNCH_PASS(true, false); }
+    else { if (tfast) B200_LAUNCH_PASS(false, true); else B200_LAUNCH_PASS(false, false); }
+#undef B200_LAUNCH_PASS
+    ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// computeH on device buffers a,b,c (each 2^L elements, already zero-padded); result in a.
+int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L) {
+  const size_t n = (size_t)1 << L;
+  int ev = 0;
+  auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], ctx->stream); };
+  // warm the tables outside the timed phases
+  B200_TRY(ensure_twiddles(ctx, L));
+  B200_TRY(ensure_coset(ctx, L));
+  mark();
+  Fr* v[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) B200_TRY(ntt_device(ctx, v[i], L, 1, true, false, B200G16_DIF));
+  mark();
+  for (int i = 0; i < 3; i++) B200_TRY(ntt_device(ctx, v[i], L, 1, false, true, B200G16_DIT));
+  mark();
+  const uint32_t g[8] = B200_FR_GEN;
+  Fr den = Fr::inv(Fr::sub(fr_pow_u64(fr_from_limbs(g), (uint64_t)n), Fr::one()));
+  k_h_pointwise<<<cdiv_u(n, 256), 256, 0, ctx->stream>>>(a, b, c, (uint32_t)n, den);
+  ctx->launches++;
+  mark();
+  B200_TRY(ntt_device(ctx, a, L, 1, true, true, B200G16_DIF));
+  mark();
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  return 0;
+}
+
+}  // namespace b200

@@ -50,6 +50,15 @@ SIGNATURES = {
     "b200g16_msm_g2": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g1_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g2_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_ntt": (C.c_int, [_vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int]),
+    "b200g16_ntt_dev": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]),
+    "b200g16_compute_h": (C.c_int, [_vp, _vp, _vp, _vp, _sz, C.c_uint, _vp]),
+    "b200g16_compute_h_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint]),
+    "b200g16_keccak_f_batch": (C.c_int, [_vp, _vp, _sz]),
+    "b200g16_keccak_f_batch_dev": (C.c_int, [_vp, _vp, _sz]),
+    "b200g16_keccak_sponge_batch": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz]),
+    "b200g16_keccak_merkle_paths": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint, _sz, _vp, _vp, _vp]),
+    "b200g16_keccak_merkle_paths_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint, _sz, _vp, _vp, _vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -202,6 +211,63 @@ class Context:
         ms = C.c_float()
         _check(load().b200g16_modmul_probe(self.h, blocks_per_sm, chains, iters, C.byref(rate), C.byref(ms)))
         return rate.value, ms.value
+
+    # -- NTT / computeH (mirror fft.Domain.FFT / FFTInverse and prove.go computeH)
+    def ntt(self, data, inverse=False, coset=False, decimation=DIF):
+        """data: (N,4) uint64 Montgomery, N a power of two; returns the transformed copy."""
+        a = _u64(data, 4).copy()
+        n = a.shape[0]
+        if n == 0 or n & (n - 1):
+            raise B200Error("ntt: length must be a power of two")
+        _check(load().b200g16_ntt(self.h, _ptr(a), n.bit_length() - 1, int(inverse), int(coset), int(decimation)))
+        return a
+
+    def ntt_dev(self, d_ptr, log2n, batch=1, inverse=False, coset=False, decimation=DIF):
+        _check(load().b200g16_ntt_dev(self.h, _vp(int(d_ptr)), log2n, batch, int(inverse), int(coset), int(decimation)))
+
+    def compute_h(self, a, b, c, log2n):
+        a, b, c = _u64(a, 4), _u64(b, 4), _u64(c, 4)
+        h = np.zeros((1 << log2n, 4), dtype=np.uint64)
+        _check(load().b200g16_compute_h(self.h, _ptr(a), _ptr(b), _ptr(c), a.shape[0], log2n, _ptr(h)))
+        return h
+
+    def compute_h_dev(self, d_a, d_b, d_c, log2n):
+        _check(load().b200g16_compute_h_dev(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)), log2n))
+
+    # -- Keccak (mirror keccakf.Permute, keccakSponge.Digest, VerifyMerkleTreeProofs)
+    def keccak_f_batch(self, states):
+        st = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 25).copy()
+        _check(load().b200g16_keccak_f_batch(self.h, _ptr(st), st.shape[0]))
+        return st
+
+    def keccak_f_batch_dev(self, d_ptr, n):
+        _check(load().b200g16_keccak_f_batch_dev(self.h, _vp(int(d_ptr)), n))
+
+    def keccak_sponge_batch(self, inputs, out_len):
+        """inputs: (n, in_len) uint8 -> (n, out_len) uint8"""
+        a = np.ascontiguousarray(inputs, dtype=np.uint8)
+        n, in_len = a.shape
+        out = np.zeros((n, out_len), dtype=np.uint8)
+        _check(load().b200g16_keccak_sponge_batch(self.h, _ptr(a), in_len, n, _ptr(out), out_len))
+        return out
+
+    def keccak_merkle_paths(self, leaves, siblings, auth_paths, indexes, expected_root=None):
+        """leaves (n, leaf_len) u8; siblings (n, 32) u8; auth_paths (n, height-1, 32) u8;
+        indexes (n,) u64 -> (roots (n,32) u8, ok (n,) bool or None)"""
+        leaves = np.ascontiguousarray(leaves, dtype=np.uint8)
+        siblings = np.ascontiguousarray(siblings, dtype=np.uint8)
+        auth_paths = np.ascontiguousarray(auth_paths, dtype=np.uint8)
+        indexes = np.ascontiguousarray(indexes, dtype=np.uint64)
+        n, leaf_len = leaves.shape
+        height = auth_paths.shape[1] + 1
+        roots = np.zeros((n, 32), dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8) if expected_root is not None else None
+        er = np.frombuffer(bytes(expected_root), dtype=np.uint8).copy() if expected_root is not None else None
+        _check(load().b200g16_keccak_merkle_paths(
+            self.h, _ptr(leaves), leaf_len, _ptr(siblings), _ptr(auth_paths) if auth_paths.size else None,
+            _ptr(indexes), height, n, _ptr(er) if er is not None else None, _ptr(roots),
+            _ptr(ok) if ok is not None else None))
+        return roots, (ok.astype(bool) if ok is not None else None)
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
     def msm(self, bases, scalars, offset=0, n=None):

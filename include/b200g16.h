@@ -113,6 +113,60 @@ int b200g16_msm_g1_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offs
 int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
                        const void* d_scalars, size_t n, uint64_t out_affine[16]);
 
+/* ---- Fr NTT / computeH -------------------------------------------------------------- */
+/* In-place transform of 2^log2n fr.Elements (HOST memory) with gnark-crypto's conventions.
+ * Replaces ecc/bn254/fr/fft (*Domain).FFT (inverse=0) / (*Domain).FFTInverse (inverse=1)
+ * with decimation fft.DIF / fft.DIT and, when coset != 0, the fft.OnCoset() option
+ * (coset shift = fr multiplicative generator 5, as fft.NewDomain defaults).
+ * The domain (generator w = w28^(2^(28-log2n)), 1/N, coset tables) is derived from
+ * log2n and cached on the ctx, like pk.Domain. */
+int b200g16_ntt(b200g16_ctx* ctx, uint64_t* data, unsigned log2n, int inverse, int coset, int decimation);
+/* Same on `batch` consecutive vectors already resident in DEVICE memory. */
+int b200g16_ntt_dev(b200g16_ctx* ctx, void* d_data, unsigned log2n, unsigned batch, int inverse, int coset,
+                    int decimation);
+/* h = computeH(a, b, c, domain): replaces gnark backend/groth16/bn254/prove.go computeH.
+ * a, b, c: n_constraints fr.Elements each (the solver's L.w, R.w, O.w; host); they are
+ * zero-padded to N = 2^log2n.  h_out receives N elements in BIT-REVERSED order, exactly
+ * what gnark feeds to the Z MSM (first N-1 entries). */
+int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                      size_t n_constraints, unsigned log2n, uint64_t* h_out);
+/* Same on zero-padded DEVICE vectors of N elements; h overwrites d_a (b, c are clobbered). */
+int b200g16_compute_h_dev(b200g16_ctx* ctx, void* d_a, void* d_b, void* d_c, unsigned log2n);
+
+/* ---- batched Keccak-f[1600] / duplex sponge / Merkle paths ---------------------------- */
+/* Permute n independent 200-byte states (25 little-endian u64 lanes, lane = x + 5y) in
+ * place.  Replaces gnark std/permutation/keccakf.Permute as called from the reference's
+ * keccakSponge/keccakSponge.go:48,69. */
+int b200g16_keccak_f_batch(b200g16_ctx* ctx, uint64_t* states, size_t n);
+int b200g16_keccak_f_batch_dev(b200g16_ctx* ctx, void* d_states, size_t n);
+/* n independent sponges: NewKeccak(); Absorb(inputs[i*in_len : (i+1)*in_len]);
+ * Squeeze(out_len) -> outputs[i*out_len ...].  Exactly keccakSponge.Digest
+ * (keccakSponge.go:17-75): rate 136, overwrite-mode absorb, no padding. */
+int b200g16_keccak_sponge_batch(b200g16_ctx* ctx, const uint8_t* inputs, size_t in_len, size_t n,
+                                uint8_t* outputs, size_t out_len);
+/* Recompute n_paths Merkle roots.  Mirrors VerifyMerkleTreeProofs
+ * (/root/reference/mtUtilities.go:109-141) with the 2-to-1 hash instantiated by the Keccak
+ * duplex above (leaf hash = sponge over the leaf's bytes, node = sponge over left||right,
+ * 32-byte digests):
+ *   leaves      n_paths x leaf_len bytes  (leaf_len a multiple of 8; field elements are 32 B)
+ *   siblings    n_paths x 32 bytes        LeafSiblingHashes (level 0)
+ *   auth_paths  n_paths x (height-1) x 32 AuthPaths, leaf-side first (level k uses entry k-1)
+ *   indexes     n_paths u64               leaf indexes; bit k set => node at level k is the
+ *                                         RIGHT child
+ *   height      tree height (= len(authPath)+1, mtUtilities.go:113)
+ * roots_out (n_paths x 32, may be NULL) receives the recomputed roots; ok_out (n_paths
+ * bytes, may be NULL) receives 1 where the root equals expected_root (32 bytes) — the
+ * AssertIsEqual at mtUtilities.go:138. */
+int b200g16_keccak_merkle_paths(b200g16_ctx* ctx, const uint8_t* leaves, size_t leaf_len,
+                                const uint8_t* siblings, const uint8_t* auth_paths,
+                                const uint64_t* indexes, unsigned height, size_t n_paths,
+                                const uint8_t* expected_root, uint8_t* roots_out, uint8_t* ok_out);
+/* Same with every buffer already in DEVICE memory (8-byte aligned). */
+int b200g16_keccak_merkle_paths_dev(b200g16_ctx* ctx, const void* d_leaves, size_t leaf_len,
+                                    const void* d_siblings, const void* d_auth_paths,
+                                    const void* d_indexes, unsigned height, size_t n_paths,
+                                    const void* d_expected_root, void* d_roots_out, void* d_ok_out);
+
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);
