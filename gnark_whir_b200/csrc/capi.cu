@@ -11,7 +11,7 @@ template <class F>
 int fixed_base_mul_device(b200g16_ctx* ctx, const Affine<F>& base, const Fr* d_scalars, size_t n, Affine<F>* d_out);
 int modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, double* modmul_per_s, float* ms_out);
 int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation);
-int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L);
+int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
 int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n);
 int sponge_batch_device(b200g16_ctx* ctx, const uint8_t* d_in, size_t in_len, size_t n, uint8_t* d_out, size_t out_len);
 int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_len, const uint64_t* d_sib,
@@ -280,7 +280,7 @@ int b200g16_compute_h_dev(b200g16_ctx* ctx, void* d_a, void* d_b, void* d_c, uns
   std::lock_guard<std::mutex> lock(ctx->mu);
   B200_CUDA(cudaSetDevice(ctx->device));
   return compute_h_device(ctx, reinterpret_cast<Fr*>(d_a), reinterpret_cast<Fr*>(d_b), reinterpret_cast<Fr*>(d_c),
-                          (int)log2n);
+                          (int)log2n, true);
 }
 
 int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
@@ -300,7 +300,7 @@ int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, co
       B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (n - n_constraints) * sizeof(Fr),
                                 ctx->stream));
   }
-  B200_TRY(compute_h_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), (int)log2n));
+  B200_TRY(compute_h_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), (int)log2n, true));
   B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, n * sizeof(Fr), cudaMemcpyDeviceToHost));
   return 0;
 }

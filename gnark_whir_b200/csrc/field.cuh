@@ -17,12 +17,14 @@ namespace b200 {
 
 struct FpTag {
   static constexpr uint32_t INV = FpParams::INV;
+  static constexpr uint64_t INV64 = 0x87d20782e4866389ull;  // -p^-1 mod 2^64
   static B200_HD constexpr uint32_t mod(int i) { constexpr uint32_t m[8] = B200_FP_MOD; return m[i]; }
   static B200_HD constexpr uint32_t one(int i) { constexpr uint32_t m[8] = B200_FP_ONE; return m[i]; }
   static B200_HD constexpr uint32_t r2(int i) { constexpr uint32_t m[8] = B200_FP_R2; return m[i]; }
 };
 struct FrTag {
   static constexpr uint32_t INV = FrParams::INV;
+  static constexpr uint64_t INV64 = 0xc2e1f593efffffffull;  // -r^-1 mod 2^64
   static B200_HD constexpr uint32_t mod(int i) { constexpr uint32_t m[8] = B200_FR_MOD; return m[i]; }
   static B200_HD constexpr uint32_t one(int i) { constexpr uint32_t m[8] = B200_FR_ONE; return m[i]; }
   static B200_HD constexpr uint32_t r2(int i) { constexpr uint32_t m[8] = B200_FR_R2; return m[i]; }
@@ -156,7 +158,9 @@ struct alignas(16) Field {
     hi[N - 1] = ptx::addc(hi[N - 1], 0);
   }
 
-  static B200_HD Field mul(const Field& a, const Field& b) {
+  // The device multiplier.  Compiled for the host too (through ptx.cuh's emulation) so the
+  // CPU test-suite can pin the exact instruction sequence the GPU executes.
+  static B200_HD Field mul_ptx(const Field& a, const Field& b) {
     uint32_t even[N], odd[N];
     mad_n_redc<true>(even, odd, a.l, b.l[0]);
     mad_n_redc<false>(odd, even, a.l, b.l[1]);
@@ -172,6 +176,63 @@ struct alignas(16) Field {
     r.l[N - 1] = ptx::addc(even[N - 1], 0);
     reduce_once(r);
     return r;
+  }
+#if !defined(__CUDA_ARCH__)
+  // Host multiplier: 4 x 64-bit CIOS on unsigned __int128 (the host finishes every MSM with a
+  // Horner pass and the proof with a handful of scalar multiplications).
+  static inline Field mul_host64(const Field& a, const Field& b) {
+    typedef unsigned __int128 u128;
+    uint64_t A[4], B[4], M[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+      A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+      B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+      M[i] = (uint64_t)T::mod(2 * i) | ((uint64_t)T::mod(2 * i + 1) << 32);
+    }
+    for (int i = 0; i < 4; i++) {
+      uint64_t carry = 0;
+      for (int j = 0; j < 4; j++) {
+        u128 p = (u128)A[j] * B[i] + t[j] + carry;
+        t[j] = (uint64_t)p;
+        carry = (uint64_t)(p >> 64);
+      }
+      u128 q = (u128)t[4] + carry;
+      t[4] = (uint64_t)q;
+      t[5] = (uint64_t)(q >> 64);
+      uint64_t m = t[0] * T::INV64;
+      u128 p = (u128)m * M[0] + t[0];
+      carry = (uint64_t)(p >> 64);
+      for (int j = 1; j < 4; j++) {
+        p = (u128)m * M[j] + t[j] + carry;
+        t[j - 1] = (uint64_t)p;
+        carry = (uint64_t)(p >> 64);
+      }
+      q = (u128)t[4] + carry;
+      t[3] = (uint64_t)q;
+      t[4] = t[5] + (uint64_t)(q >> 64);
+    }
+    // t < 2m: subtract m once if needed
+    uint64_t d[4], borrow = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 x = (u128)t[i] - M[i] - borrow;
+      d[i] = (uint64_t)x;
+      borrow = (uint64_t)(x >> 64) & 1;
+    }
+    bool ge = t[4] != 0 || borrow == 0;
+    Field r;
+    for (int i = 0; i < 4; i++) {
+      uint64_t v = ge ? d[i] : t[i];
+      r.l[2 * i] = (uint32_t)v;
+      r.l[2 * i + 1] = (uint32_t)(v >> 32);
+    }
+    return r;
+  }
+#endif
+  static B200_HD Field mul(const Field& a, const Field& b) {
+#if defined(__CUDA_ARCH__)
+    return mul_ptx(a, b);
+#else
+    return mul_host64(a, b);
+#endif
   }
   static B200_HD Field sqr(const Field& a) { return mul(a, a); }
 

@@ -140,7 +140,7 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
                    uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
                    uint32_t* entries, uint32_t* task_bucket, int* ev) {
   cudaStream_t st = ctx->stream;
-  auto mark = [&]() { if (*ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
+  auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
   mark();
   B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * sizeof(uint32_t), st));
   k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.nbw, digits, counts);

@@ -181,11 +181,20 @@ __global__ void __launch_bounds__(128) k_reduce2(const XYZZ<F>* __restrict__ chu
 }
 
 // ------------------------------------------------------------------------------ host driver
+constexpr int MSM_SLOTS = 8;           // independent result slots (a prove enqueues 5 MSMs back to back)
+constexpr int MSM_MAX_WINDOWS = 130;
+
+// Enqueue one MSM on ctx->stream; its W window sums land in pinned slot `slot` once the stream
+// drains.  No host synchronisation.  record_events: fill ctx->ev for b200g16_last_timings.
 template <class F>
-int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, Affine<F>* out) {
-  if (n == 0) { *out = Affine<F>::inf(); return 0; }
-  if (n >= (1ull << 31)) return fail(B200G16_ERR_ARG, "msm: n=%zu too large", n);
+int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, int slot, MsmCfg* cfg_out,
+                bool record_events) {
   MsmCfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  *cfg_out = cfg;
+  if (slot < 0 || slot >= MSM_SLOTS) return fail(B200G16_ERR_ARG, "msm: bad slot");
+  if (n == 0) return 0;  // cfg.W == 0 marks "infinity"
+  if (n >= (1ull << 31)) return fail(B200G16_ERR_ARG, "msm: n=%zu too large", n);
   cfg.c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(n);
   if (cfg.c < 2 || cfg.c > 24) return fail(B200G16_ERR_ARG, "msm: window %d out of range", cfg.c);
   cfg.W = msm_num_windows(cfg.c);
@@ -210,12 +219,13 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, 
   B200_TRY(ws.buckets.ensure((size_t)cfg.nb * sizeof(XYZZ<F>)));
   B200_TRY(ws.chunks.ensure((size_t)cfg.W * cfg.nch * sizeof(XYZZ<F>)));
   B200_TRY(ws.windows.ensure((size_t)cfg.W * sizeof(XYZZ<F>)));
-  if (ws.pinned_cap < 130 * sizeof(XYZZ<Fp2>)) {
+  const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
+  if (ws.pinned_cap < MSM_SLOTS * slot_bytes) {
     if (ws.pinned) cudaFreeHost(ws.pinned);
-    B200_CUDA(cudaMallocHost(&ws.pinned, 130 * sizeof(XYZZ<Fp2>)));
-    ws.pinned_cap = 130 * sizeof(XYZZ<Fp2>);
+    B200_CUDA(cudaMallocHost(&ws.pinned, MSM_SLOTS * slot_bytes));
+    ws.pinned_cap = MSM_SLOTS * slot_bytes;
   }
-  if (cfg.W > 128) return fail(B200G16_ERR_ARG, "msm: too many windows");
+  if (cfg.W > MSM_MAX_WINDOWS - 2) return fail(B200G16_ERR_ARG, "msm: too many windows");
 
   uint32_t* counts = ws.counts.as<uint32_t>();
   uint32_t* offsets = counts + cfg.nb;
@@ -233,10 +243,10 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, 
   cudaStream_t st = ctx->stream;
   uint32_t n32 = (uint32_t)n;
   int ev = 0;
-  auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
+  auto mark = [&]() { if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
 
   B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
-                          task_bucket, &ev));
+                          task_bucket, record_events ? &ev : nullptr));
   k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_bucket, offsets, counts, task_off,
                                                          totals, cfg.seg, partials);
   mark();
@@ -250,13 +260,20 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, 
   mark();
   ctx->launches += 5;
   B200_CUDA(cudaGetLastError());
-  B200_CUDA(cudaMemcpyAsync(ws.pinned, windows, (size_t)cfg.W * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaStreamSynchronize(st));
-  ctx->timings.n = ev - 1;
-  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.W * sizeof(XYZZ<F>),
+                            cudaMemcpyDeviceToHost, st));
+  if (record_events) ctx->timings.n = -(ev - 1);  // negative: events recorded, not yet resolved
+  *cfg_out = cfg;
+  return 0;
+}
 
-  // Horner over windows on the host: acc = sum_w 2^(c w) * S_w
-  const XYZZ<F>* hw = reinterpret_cast<const XYZZ<F>*>(ws.pinned);
+// After the stream has drained: Horner over the window sums of `slot` on the host,
+// acc = sum_w 2^(c w) * S_w, then one inversion to the affine normal form.
+template <class F>
+int msm_collect(b200g16_ctx* ctx, int slot, const MsmCfg& cfg, Affine<F>* out) {
+  if (cfg.W == 0) { *out = Affine<F>::inf(); return 0; }
+  const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
+  const XYZZ<F>* hw = reinterpret_cast<const XYZZ<F>*>((const char*)ctx->msm.pinned + (size_t)slot * slot_bytes);
   XYZZ<F> acc = hw[cfg.W - 1];
   for (int w = cfg.W - 2; w >= 0; w--) {
     for (int k = 0; k < cfg.c; k++) acc.dbl();
@@ -264,6 +281,23 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, 
   }
   *out = acc.to_affine();
   return 0;
+}
+
+inline void msm_resolve_timings(b200g16_ctx* ctx) {
+  if (ctx->timings.n >= 0) return;
+  int n = -ctx->timings.n;
+  for (int i = 0; i < n; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  ctx->timings.n = n;
+}
+
+template <class F>
+int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, Affine<F>* out) {
+  MsmCfg cfg;
+  ctx->timings.n = 0;
+  B200_TRY(msm_enqueue<F>(ctx, d_bases, d_scalars, n, 0, &cfg, true));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  msm_resolve_timings(ctx);
+  return msm_collect<F>(ctx, 0, cfg, out);
 }
 
 }  // namespace b200

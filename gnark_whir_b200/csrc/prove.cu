@@ -1,0 +1,273 @@
+// Groth16 Prove, everything after the constraint solver, for one GPU.
+//
+// Replaces gnark v0.11.0 backend/groth16/bn254/prove.go Prove() from "go computeH" to
+// "return proof" (steps 4-9 of SURVEY §3.2), as called by the reference at
+// /root/reference/mt.go:496.  The BSB22 Pedersen commitment / proof of knowledge, which
+// gnark computes inside and right after Solve, go through b200g16_msm_g1 on resident
+// pedersen bases (they are ordinary G1 MSMs).
+//
+// Device timeline (one stream): H2D(wires,a,b,c) -> gather wire values into the A / B / K
+// scalar vectors (gnark's filter by pk.InfinityA / pk.InfinityB and by public+committed wires)
+// -> computeH -> MSM A, B1, K, Z (scalars = h, straight from computeH's device buffer), B2
+// enqueued back to back -> one synchronisation -> host: Horner per MSM, then
+//   Ar  = A + alpha + r*delta
+//   Bs1 = B1 + beta + s*delta           Bs = B2 + beta2 + s*delta2
+//   Krs = K + Z + (-rs)*delta + s*Ar + r*Bs1
+#include "msm_impl.cuh"
+
+namespace b200 {
+int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
+// instantiated in msm_g1.cu / msm_g2.cu
+extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
+extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
+}  // namespace b200
+
+struct b200g16_pk {
+  int device = 0;
+  unsigned log2n = 0;
+  size_t n_wires = 0;
+  // resident point vectors; owned[i] tells whether pk_free releases them
+  b200g16_bases* vec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B1, K, Z, B2
+  bool owned[5] = {false, false, false, false, false};
+  b200::G1Affine alpha, beta, delta;
+  b200::G2Affine beta2, delta2;
+  // wire -> scalar-vector gather lists (device): A, B, K
+  uint32_t* d_idx[3] = {nullptr, nullptr, nullptr};
+  size_t n_idx[3] = {0, 0, 0};
+};
+
+namespace b200 {
+
+__global__ void __launch_bounds__(256) k_gather_fr(const Fr* __restrict__ src, const uint32_t* __restrict__ idx,
+                                                    uint32_t n, Fr* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + idx[i]);
+  uint4* d = reinterpret_cast<uint4*>(dst + i);
+  d[0] = __ldg(s);
+  d[1] = __ldg(s + 1);
+}
+
+template <class F>
+static Affine<F> host_scalar_mul_aff(const Affine<F>& p, const Fr& k_mont) {
+  Fr s = Fr::from_mont(k_mont);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  int top = 255;
+  while (top >= 0 && !((s.l[top >> 5] >> (top & 31)) & 1)) top--;
+  for (int i = top; i >= 0; i--) {
+    acc.dbl();
+    if ((s.l[i >> 5] >> (i & 31)) & 1) acc.madd(p);
+  }
+  return acc.to_affine();
+}
+
+template <class F>
+static Affine<F> host_sum(std::initializer_list<Affine<F>> pts) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (const auto& p : pts) acc.madd(p);
+  return acc.to_affine();
+}
+
+static int build_index(const uint8_t* skip, size_t n_wires, size_t expect, uint32_t** d_out, const char* what) {
+  std::vector<uint32_t> idx;
+  idx.reserve(expect);
+  for (size_t i = 0; i < n_wires; i++)
+    if (!skip[i]) idx.push_back((uint32_t)i);
+  if (idx.size() != expect)
+    return fail(B200G16_ERR_ARG, "pk_upload: %s flags keep %zu wires but the point vector has %zu", what, idx.size(),
+                expect);
+  B200_CUDA(cudaMalloc(d_out, (idx.size() ? idx.size() : 1) * sizeof(uint32_t)));
+  if (!idx.empty())
+    B200_CUDA(cudaMemcpy(*d_out, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static void pk_release(b200g16_pk* pk) {
+  if (!pk) return;
+  cudaSetDevice(pk->device);
+  for (int i = 0; i < 5; i++)
+    if (pk->owned[i] && pk->vec[i]) b200g16_bases_free(pk->vec[i]);
+  for (int i = 0; i < 3; i++)
+    if (pk->d_idx[i]) cudaFree(pk->d_idx[i]);
+  delete pk;
+}
+
+static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out) {
+  if (!ctx || !d || !out) return fail(B200G16_ERR_ARG, "pk_upload: null");
+  if (!d->g1_alpha || !d->g1_beta || !d->g1_delta || !d->g2_beta || !d->g2_delta)
+    return fail(B200G16_ERR_ARG, "pk_upload: alpha/beta/delta missing");
+  if (!d->infinity_a || !d->infinity_b || !d->k_skip) return fail(B200G16_ERR_ARG, "pk_upload: wire flags missing");
+  if (d->log2_domain > 28) return fail(B200G16_ERR_ARG, "pk_upload: domain 2^%u exceeds two-adicity", d->log2_domain);
+  if (d->n_wires >= (1ull << 32)) return fail(B200G16_ERR_ARG, "pk_upload: too many wires");
+  b200g16_pk* pk = new b200g16_pk();
+  pk->device = ctx->device;
+  pk->log2n = d->log2_domain;
+  pk->n_wires = d->n_wires;
+  const uint64_t* host[5] = {d->g1_a, d->g1_b, d->g1_k, d->g1_z, d->g2_b};
+  const b200g16_bases* res[5] = {d->res_a, d->res_b, d->res_k, d->res_z, d->res_b2};
+  const size_t n[5] = {d->n_a, d->n_b, d->n_k, d->n_z, d->n_b};
+  for (int i = 0; i < 5; i++) {
+    if (res[i]) {
+      if (res[i]->n != n[i] || res[i]->group != (i == 4 ? 2 : 1) || res[i]->device != ctx->device) {
+        pk_release(pk);
+        return fail(B200G16_ERR_ARG, "pk_upload: resident vector %d has the wrong size/group/device", i);
+      }
+      pk->vec[i] = const_cast<b200g16_bases*>(res[i]);
+    } else {
+      if (n[i] && !host[i]) { pk_release(pk); return fail(B200G16_ERR_ARG, "pk_upload: vector %d missing", i); }
+      int st = (i == 4) ? b200g16_bases_upload_g2(ctx, host[i], n[i], &pk->vec[i])
+                        : b200g16_bases_upload_g1(ctx, host[i], n[i], &pk->vec[i]);
+      if (st) { pk_release(pk); return st; }
+      pk->owned[i] = true;
+    }
+  }
+  size_t N = (size_t)1 << d->log2_domain;
+  if (d->n_z + 1 != N) { pk_release(pk); return fail(B200G16_ERR_ARG, "pk_upload: len(Z)=%zu, want N-1=%zu", d->n_z, N - 1); }
+  memcpy(&pk->alpha, d->g1_alpha, sizeof(G1Affine));
+  memcpy(&pk->beta, d->g1_beta, sizeof(G1Affine));
+  memcpy(&pk->delta, d->g1_delta, sizeof(G1Affine));
+  memcpy(&pk->beta2, d->g2_beta, sizeof(G2Affine));
+  memcpy(&pk->delta2, d->g2_delta, sizeof(G2Affine));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  const uint8_t* flags[3] = {d->infinity_a, d->infinity_b, d->k_skip};
+  const size_t expect[3] = {d->n_a, d->n_b, d->n_k};
+  const char* names[3] = {"InfinityA", "InfinityB", "k_skip"};
+  for (int i = 0; i < 3; i++) {
+    int st = build_index(flags[i], d->n_wires, expect[i], &pk->d_idx[i], names[i]);
+    if (st) { pk_release(pk); return st; }
+    pk->n_idx[i] = expect[i];
+  }
+  *out = pk;
+  return 0;
+}
+
+// d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
+static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, Fr* d_a, Fr* d_b, Fr* d_c,
+                        const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io) {
+  cudaStream_t st = ctx->stream;
+  int ev = *ev_io;
+  auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
+  // scalar vectors
+  size_t tot = pk->n_idx[0] + pk->n_idx[1] + pk->n_idx[2];
+  B200_TRY(ctx->io_b.ensure((tot ? tot : 1) * sizeof(Fr)));
+  Fr* sv[3];
+  sv[0] = ctx->io_b.as<Fr>();
+  sv[1] = sv[0] + pk->n_idx[0];
+  sv[2] = sv[1] + pk->n_idx[1];
+  for (int i = 0; i < 3; i++)
+    if (pk->n_idx[i]) {
+      k_gather_fr<<<cdiv(pk->n_idx[i], 256), 256, 0, st>>>(d_wires, pk->d_idx[i], (uint32_t)pk->n_idx[i], sv[i]);
+      ctx->launches++;
+    }
+  mark();
+  B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
+  mark();
+  MsmCfg cfg[5];
+  const size_t N = (size_t)1 << pk->log2n;
+  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[0]->d_points, sv[0], pk->n_idx[0], 0, &cfg[0], false));
+  mark();
+  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[1]->d_points, sv[1], pk->n_idx[1], 1, &cfg[1], false));
+  mark();
+  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[2]->d_points, sv[2], pk->n_idx[2], 2, &cfg[2], false));
+  mark();
+  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[3]->d_points, d_a, N - 1, 3, &cfg[3], false));
+  mark();
+  B200_TRY(msm_enqueue<Fp2>(ctx, (const G2Affine*)pk->vec[4]->d_points, sv[1], pk->n_idx[1], 4, &cfg[4], false));
+  mark();
+  B200_CUDA(cudaStreamSynchronize(st));
+  *ev_io = ev;
+
+  G1Affine A, B1, K, Z;
+  G2Affine B2;
+  B200_TRY(msm_collect<Fp>(ctx, 0, cfg[0], &A));
+  B200_TRY(msm_collect<Fp>(ctx, 1, cfg[1], &B1));
+  B200_TRY(msm_collect<Fp>(ctx, 2, cfg[2], &K));
+  B200_TRY(msm_collect<Fp>(ctx, 3, cfg[3], &Z));
+  B200_TRY(msm_collect<Fp2>(ctx, 4, cfg[4], &B2));
+
+  Fr kr = Fr::neg(Fr::mul(r, s));
+  G1Affine ar = host_sum<Fp>({A, pk->alpha, host_scalar_mul_aff<Fp>(pk->delta, r)});
+  G1Affine bs1 = host_sum<Fp>({B1, pk->beta, host_scalar_mul_aff<Fp>(pk->delta, s)});
+  G1Affine krs = host_sum<Fp>({K, Z, host_scalar_mul_aff<Fp>(pk->delta, kr), host_scalar_mul_aff<Fp>(ar, s),
+                               host_scalar_mul_aff<Fp>(bs1, r)});
+  G2Affine bs = host_sum<Fp2>({B2, pk->beta2, host_scalar_mul_aff<Fp2>(pk->delta2, s)});
+  memcpy(out->ar, &ar, 64);
+  memcpy(out->bs, &bs, 128);
+  memcpy(out->krs, &krs, 64);
+  memcpy(out->msm_a, &A, 64);
+  memcpy(out->msm_b1, &B1, 64);
+  memcpy(out->msm_k, &K, 64);
+  memcpy(out->msm_z, &Z, 64);
+  memcpy(out->msm_b2, &B2, 128);
+  memcpy(out->bs1, &bs1, 64);
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200g16_pk_upload(b200g16_ctx* ctx, const b200g16_pk_desc* desc, b200g16_pk** out) { return pk_build(ctx, desc, out); }
+
+void b200g16_pk_free(b200g16_pk* pk) { pk_release(pk); }
+
+int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires, size_t n_wires, const uint64_t* a,
+                  const uint64_t* b, const uint64_t* c, size_t n_constraints, const uint64_t r[4], const uint64_t s[4],
+                  b200g16_proof* proof_out, uint64_t* h_out) {
+  if (!ctx || !pk || !wires || !a || !b || !c || !r || !s || !proof_out) return fail(B200G16_ERR_ARG, "prove: null");
+  if (pk->device != ctx->device) return fail(B200G16_ERR_STATE, "prove: pk lives on another device");
+  if (n_wires != pk->n_wires) return fail(B200G16_ERR_ARG, "prove: %zu wires, pk expects %zu", n_wires, pk->n_wires);
+  const size_t N = (size_t)1 << pk->log2n;
+  if (n_constraints > N) return fail(B200G16_ERR_ARG, "prove: %zu constraints > domain %zu", n_constraints, N);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int ev = 0;
+  cudaEventRecord(ctx->ev[ev++], st);
+  B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
+  B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  DevBuf* bufs[3] = {&ctx->ntt.a, &ctx->ntt.b, &ctx->ntt.c};
+  const uint64_t* src[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    B200_TRY(bufs[i]->ensure(N * sizeof(Fr)));
+    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (N > n_constraints)
+      B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), st));
+  }
+  cudaEventRecord(ctx->ev[ev++], st);
+  Fr fr_r, fr_s;
+  memcpy(&fr_r, r, 32);
+  memcpy(&fr_s, s, 32);
+  B200_TRY(prove_device(ctx, pk, ctx->io_a.as<Fr>(), ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(),
+                        fr_r, fr_s, proof_out, &ev));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  if (h_out) B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200g16_prove_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_a, void* d_b, void* d_c,
+                      const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out) {
+  if (!ctx || !pk || !d_wires || !d_a || !d_b || !d_c || !r || !s || !proof_out)
+    return fail(B200G16_ERR_ARG, "prove_dev: null");
+  if (pk->device != ctx->device) return fail(B200G16_ERR_STATE, "prove_dev: pk lives on another device");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  int ev = 0;
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  Fr fr_r, fr_s;
+  memcpy(&fr_r, r, 32);
+  memcpy(&fr_s, s, 32);
+  B200_TRY(prove_device(ctx, pk, (const Fr*)d_wires, (Fr*)d_a, (Fr*)d_b, (Fr*)d_c, fr_r, fr_s, proof_out, &ev));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+"""Host-side mirror of gnark's groth16 API for BN254, on top of libb200g16.
+
+Same entry points, argument meaning and flow as the calls the reference makes at
+/root/reference/mt.go:448 (groth16.Setup), mt.go:496 (groth16.Prove) and mt.go:497
+(groth16.Verify); gnark v0.11.0 backend/groth16/bn254/{setup,prove}.go is the behaviour
+restated.  What runs where:
+
+  Setup   host: toxic waste, per-wire A_i(tau), B_i(tau), C_i(tau), K_i, Z_i scalars (python ints)
+          GPU : every group element, through b200g16_fixed_base_mul_g1/g2
+  Prove   host: the constraint "solver" (here: L.w, R.w, O.w from a full assignment), the BSB22
+                challenge hash, sampling r, s
+          GPU : Pedersen commit + PoK (b200g16_msm_g1), computeH, the five MSMs, via b200g16_prove
+  Verify  not built yet; tests verify proofs with the oracle's pairing.
+
+The host language would be Go (a cgo shim) if a Go toolchain existed in this
+image; this module is the same marshalling in Python over ctypes.  There is no CPU fallback:
+every group operation below goes through the CUDA library.
+"""
+from __future__ import annotations
+
+import hashlib
+import secrets
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import lib
+
+R_MOD = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+P_MOD = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+_ROOT_2_28 = 19103219067921713944291392827692070036145651957329286315305642004821462161904
+_MONT = 1 << 256
+_M64 = (1 << 64) - 1
+
+G1_GEN = (1, 2)
+G2_GEN = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+           11559732032986387107991004021392285783925812861821192530917403151452391805634),
+          (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+           4082367875863433681332203403145435568316851327593401208105741076214120093531))
+
+
+# ---------------------------------------------------------------- layout helpers (fr.Element etc.)
+def fr_array(vals):
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = v % R_MOD * _MONT % R_MOD
+        out[i] = (m & _M64, (m >> 64) & _M64, (m >> 128) & _M64, m >> 192)
+    return out
+
+
+def _fp_limbs(x):
+    m = x % P_MOD * _MONT % P_MOD
+    return [m & _M64, (m >> 64) & _M64, (m >> 128) & _M64, m >> 192]
+
+
+def g1_point(pt):
+    return np.array(_fp_limbs(pt[0]) + _fp_limbs(pt[1]), dtype=np.uint64)
+
+
+def g2_point(pt):
+    (x0, x1), (y0, y1) = pt
+    return np.array(_fp_limbs(x0) + _fp_limbs(x1) + _fp_limbs(y0) + _fp_limbs(y1), dtype=np.uint64)
+
+
+def _fp_from(limbs):
+    v = int(limbs[0]) | int(limbs[1]) << 64 | int(limbs[2]) << 128 | int(limbs[3]) << 192
+    return v * pow(_MONT, -1, P_MOD) % P_MOD
+
+
+# ---------------------------------------------------------------- constraint system (host)
+@dataclass
+class R1CS:
+    """Rank-1 system: wires [0, nb_public) public (wire 0 = 1), rest private.
+    constraints: list of (L, R, O), each [(wire, coeff)].  Optional single BSB22 commitment."""
+    nb_wires: int
+    nb_public: int
+    constraints: list
+    private_committed: list = field(default_factory=list)
+    public_committed: list = field(default_factory=list)
+    commitment_wire: int = -1
+
+
+def _lc(lc, w):
+    return sum(c * w[i] for i, c in lc) % R_MOD
+
+
+def solve_abc(r1cs, w):
+    """solution.A/B/C of gnark's r1cs.Solve for an already complete assignment."""
+    return ([_lc(L, w) for L, _, _ in r1cs.constraints],
+            [_lc(Rr, w) for _, Rr, _ in r1cs.constraints],
+            [_lc(O, w) for _, _, O in r1cs.constraints])
+
+
+# ---------------------------------------------------------------- keys / proof (gnark field names)
+@dataclass
+class PedersenProvingKey:          # gnark-crypto fr/pedersen.ProvingKey
+    Basis: np.ndarray
+    BasisExpSigma: np.ndarray
+    basis_dev: object = None
+    basis_exp_sigma_dev: object = None
+
+
+@dataclass
+class ProvingKey:                  # groth16_bn254.ProvingKey
+    log2_domain: int
+    G1_Alpha: np.ndarray
+    G1_Beta: np.ndarray
+    G1_Delta: np.ndarray
+    G1_A: object
+    G1_B: object
+    G1_Z: object
+    G1_K: object
+    G2_Beta: np.ndarray
+    G2_Delta: np.ndarray
+    G2_B: object
+    InfinityA: np.ndarray
+    InfinityB: np.ndarray
+    k_skip: np.ndarray
+    CommitmentKeys: list = field(default_factory=list)
+    _dev: object = None            # device handle, filled lazily on first Prove (like gnark's icicle pk)
+    _ctx: object = None
+
+    def device_handle(self, ctx):
+        if self._dev is None:
+            self._dev = ctx.pk_upload(self.log2_domain, len(self.InfinityA), self.G1_A, self.G1_B, self.G1_K,
+                                      self.G1_Z, self.G2_B, self.G1_Alpha, self.G1_Beta, self.G1_Delta,
+                                      self.G2_Beta, self.G2_Delta, self.InfinityA, self.InfinityB, self.k_skip)
+            self._ctx = ctx
+        return self._dev
+
+    def free(self):
+        if self._dev is not None:
+            self._ctx.pk_free(self._dev)
+            self._dev = None
+        for ck in self.CommitmentKeys:
+            for b in (ck.basis_dev, ck.basis_exp_sigma_dev):
+                if b is not None:
+                    b.free()
+            ck.basis_dev = ck.basis_exp_sigma_dev = None
+
+
+@dataclass
+class VerifyingKey:                # groth16_bn254.VerifyingKey
+    G1_Alpha: np.ndarray
+    G1_K: np.ndarray
+    G2_Beta: np.ndarray
+    G2_Gamma: np.ndarray
+    G2_Delta: np.ndarray
+    PedersenG: np.ndarray = None
+    PedersenGSigmaNeg: np.ndarray = None
+    PublicAndCommitmentCommitted: list = field(default_factory=list)
+    has_commitment: bool = False
+
+
+@dataclass
+class Proof:                       # groth16_bn254.Proof
+    Ar: np.ndarray
+    Krs: np.ndarray
+    Bs: np.ndarray
+    Commitments: list = field(default_factory=list)
+    CommitmentPok: np.ndarray = None
+    debug: dict = field(default_factory=dict)   # intermediate MSM outputs, h (parity checks)
+
+
+@dataclass
+class ToxicWaste:
+    tau: int
+    alpha: int
+    beta: int
+    gamma: int
+    delta: int
+    sigma: int
+
+    @staticmethod
+    def random():
+        return ToxicWaste(*[1 + secrets.randbelow(R_MOD - 1) for _ in range(6)])
+
+
+# ---------------------------------------------------------------- hash_to_field (RFC 9380, SHA-256)
+def _expand_xmd(msg, dst, length):
+    ell = (length + 31) // 32
+    dstp = dst + bytes([len(dst)])
+    b0 = hashlib.sha256(bytes(64) + msg + length.to_bytes(2, "big") + b"\x00" + dstp).digest()
+    bi = hashlib.sha256(b0 + b"\x01" + dstp).digest()
+    out = bi
+    for i in range(2, ell + 1):
+        bi = hashlib.sha256(bytes(x ^ y for x, y in zip(b0, bi)) + bytes([i]) + dstp).digest()
+        out += bi
+    return out[:length]
+
+
+def commitment_challenge(commitment_limbs, public_committed_values):
+    """gnark prove.go: hash_to_field("bsb22-commitment")(commitment.Marshal() || committed publics)."""
+    c = np.asarray(commitment_limbs, dtype=np.uint64)
+    if not c.any():
+        raw = bytes([0x40]) + bytes(63)
+    else:
+        raw = _fp_from(c[:4]).to_bytes(32, "big") + _fp_from(c[4:]).to_bytes(32, "big")
+    msg = raw + b"".join(int(v % R_MOD).to_bytes(32, "big") for v in public_committed_values)
+    return int.from_bytes(_expand_xmd(msg, b"bsb22-commitment", 48), "big") % R_MOD
+
+
+# ---------------------------------------------------------------- Setup
+def _bitrev(i, logn):
+    return int(format(i, "0%db" % logn)[::-1], 2) if logn else 0
+
+
+def Setup(ctx, r1cs, toxic=None):
+    """groth16.Setup(ccs) -> (pk, vk).  `toxic` may be fixed for reproducible tests."""
+    tw = toxic or ToxicWaste.random()
+    m = len(r1cs.constraints)
+    logn = max(m - 1, 0).bit_length()
+    n = 1 << logn
+    w_gen = pow(_ROOT_2_28, 1 << (28 - logn), R_MOD)
+    nw = r1cs.nb_wires
+    A, B, Cc = [0] * nw, [0] * nw, [0] * nw
+    zn = (pow(tw.tau, n, R_MOD) - 1) * pow(n, -1, R_MOD) % R_MOD
+    wj = 1
+    for L, Rr, O in r1cs.constraints:           # setupABC: Lagrange basis at tau
+        lag = zn * wj % R_MOD * pow((tw.tau - wj) % R_MOD, -1, R_MOD) % R_MOD
+        for i, c in L:
+            A[i] = (A[i] + c * lag) % R_MOD
+        for i, c in Rr:
+            B[i] = (B[i] + c * lag) % R_MOD
+        for i, c in O:
+            Cc[i] = (Cc[i] + c * lag) % R_MOD
+        wj = wj * w_gen % R_MOD
+    gi, di = pow(tw.gamma, -1, R_MOD), pow(tw.delta, -1, R_MOD)
+    committed = set(r1cs.private_committed)
+    kval = lambda i: (tw.beta * A[i] + tw.alpha * B[i] + Cc[i]) % R_MOD
+    k_priv, k_pub, k_ped = [], [], []
+    k_skip = np.ones(nw, dtype=np.uint8)
+    for i in range(nw):
+        if i < r1cs.nb_public:
+            k_pub.append(kval(i) * gi % R_MOD)
+        elif i in committed or i == r1cs.commitment_wire:
+            continue
+        else:
+            k_priv.append(kval(i) * di % R_MOD)
+            k_skip[i] = 0
+    if r1cs.commitment_wire >= 0:
+        k_pub.append(kval(r1cs.commitment_wire) * gi % R_MOD)
+        k_ped = [kval(i) * gi % R_MOD for i in r1cs.private_committed]
+    zdt = (pow(tw.tau, n, R_MOD) - 1) * di % R_MOD
+    zs, t = [], zdt
+    for _ in range(n):
+        zs.append(t)
+        t = t * tw.tau % R_MOD
+    zs = [zs[_bitrev(i, logn)] for i in range(n)][:n - 1]
+    inf_a = np.array([a == 0 for a in A], dtype=np.uint8)
+    inf_b = np.array([b == 0 for b in B], dtype=np.uint8)
+    sa, sb = [a for a in A if a], [b for b in B if b]
+    g1 = g1_point(G1_GEN)
+    g2 = g2_point(G2_GEN)
+    scal = sa + sb + zs + k_priv + k_pub + k_ped + [tw.alpha, tw.beta, tw.delta]
+    pts = ctx.fixed_base_mul(g1, fr_array(scal), group=1)      # BatchScalarMultiplicationG1
+    o = 0
+
+    def take(k):
+        nonlocal o
+        v = pts[o:o + k].copy()
+        o += k
+        return v
+    pkA, pkB, pkZ, pkK, vkK, ped = take(len(sa)), take(len(sb)), take(n - 1), take(len(k_priv)), \
+        take(len(k_pub)), take(len(k_ped))
+    alpha1, beta1, delta1 = take(3)
+    pts2 = ctx.fixed_base_mul(g2, fr_array(sb + [tw.beta, tw.delta, tw.gamma]), group=2)
+    pkB2 = pts2[:len(sb)].copy()
+    beta2, delta2, gamma2 = pts2[len(sb)], pts2[len(sb) + 1], pts2[len(sb) + 2]
+    pk = ProvingKey(logn, alpha1, beta1, delta1, pkA, pkB, pkZ, pkK, beta2, delta2, pkB2, inf_a, inf_b, k_skip)
+    vk = VerifyingKey(alpha1, vkK, beta2, gamma2, delta2)
+    if r1cs.commitment_wire >= 0:
+        # pedersen.Setup: BasisExpSigma = sigma * Basis; vk = (G, -sigma * G)
+        bes = ctx.fixed_base_mul(g1, fr_array([k * tw.sigma % R_MOD for k in k_ped]), group=1)
+        pk.CommitmentKeys = [PedersenProvingKey(ped, bes)]
+        vk.PedersenG = g2
+        vk.PedersenGSigmaNeg = ctx.fixed_base_mul(g2, fr_array([(-tw.sigma) % R_MOD]), group=2)[0]
+        vk.PublicAndCommitmentCommitted = list(r1cs.public_committed)
+        vk.has_commitment = True
+    return pk, vk
+
+
+# ---------------------------------------------------------------- Prove
+def Prove(ctx, r1cs, pk, witness, r=None, s=None, resolve=None, want_h=False):
+    """groth16.Prove(ccs, pk, fullWitness, opts...).
+
+    witness: full wire assignment (list of ints); for a circuit with a commitment the commitment
+    wire is filled here, exactly where gnark's solver would call the BSB22 hint: Pedersen-commit to
+    the committed wires on the GPU, hash, write the challenge; `resolve(witness)` then lets the
+    caller (standing in for the solver) finish wires that depend on the challenge.
+    r, s: blinding scalars; sampled like gnark does when omitted."""
+    w = list(witness)
+    proof_commitments, pok = [], None
+    if r1cs.commitment_wire >= 0:
+        ck = pk.CommitmentKeys[0]
+        if ck.basis_dev is None:
+            ck.basis_dev = ctx.upload_g1(ck.Basis)
+            ck.basis_exp_sigma_dev = ctx.upload_g1(ck.BasisExpSigma)
+        vals = fr_array([w[i] for i in r1cs.private_committed])
+        com = ctx.msm(ck.basis_dev, vals)                        # pedersen Commit (inside Solve)
+        w[r1cs.commitment_wire] = commitment_challenge(com, [w[i] for i in r1cs.public_committed])
+        if resolve is not None:
+            resolve(w)
+        pok = ctx.msm(ck.basis_exp_sigma_dev, vals)              # pedersen ProveKnowledge (1 commitment: fold = id)
+        proof_commitments = [com]
+    a, b, c = solve_abc(r1cs, w)
+    r = secrets.randbelow(R_MOD) if r is None else r
+    s = secrets.randbelow(R_MOD) if s is None else s
+    out, h = ctx.prove(pk.device_handle(ctx), fr_array(w), fr_array(a), fr_array(b), fr_array(c),
+                       fr_array([r])[0], fr_array([s])[0], want_h=want_h, log2_domain=pk.log2_domain)
+    dbg = dict(out)
+    dbg["h"] = h
+    dbg["witness"] = w
+    return Proof(out["ar"], out["krs"], out["bs"], proof_commitments, pok, dbg)
+
+
+def Verify(proof, vk, public_witness):
+    raise NotImplementedError("groth16.Verify on the B200 path is a later row (SURVEY §8f rank 3); "
+                              "tests check proofs with the oracle's independent pairing")

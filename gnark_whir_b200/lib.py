@@ -59,6 +59,10 @@ SIGNATURES = {
     "b200g16_keccak_sponge_batch": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz]),
     "b200g16_keccak_merkle_paths": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint, _sz, _vp, _vp, _vp]),
     "b200g16_keccak_merkle_paths_dev": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, C.c_uint, _sz, _vp, _vp, _vp]),
+    "b200g16_pk_upload": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "b200g16_pk_free": (None, [_vp]),
+    "b200g16_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "b200g16_prove_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -121,6 +125,30 @@ def g2_scalar_mul(p, k):
     out = np.zeros(16, dtype=np.uint64)
     _check(load().b200g16_g2_scalar_mul(_ptr(_u64(p)), _ptr(_u64(k)), _ptr(out)))
     return out
+
+
+class PkDesc(C.Structure):
+    """struct b200g16_pk_desc (include/b200g16.h)"""
+    _fields_ = [
+        ("log2_domain", C.c_uint), ("n_wires", _sz),
+        ("g1_a", _vp), ("g1_b", _vp), ("g1_k", _vp), ("g1_z", _vp), ("g2_b", _vp),
+        ("res_a", _vp), ("res_b", _vp), ("res_k", _vp), ("res_z", _vp), ("res_b2", _vp),
+        ("n_a", _sz), ("n_b", _sz), ("n_k", _sz), ("n_z", _sz),
+        ("g1_alpha", _vp), ("g1_beta", _vp), ("g1_delta", _vp), ("g2_beta", _vp), ("g2_delta", _vp),
+        ("infinity_a", _vp), ("infinity_b", _vp), ("k_skip", _vp),
+    ]
+
+
+class ProofOut(C.Structure):
+    """struct b200g16_proof (include/b200g16.h)"""
+    _fields_ = [
+        ("ar", C.c_uint64 * 8), ("bs", C.c_uint64 * 16), ("krs", C.c_uint64 * 8),
+        ("msm_a", C.c_uint64 * 8), ("msm_b1", C.c_uint64 * 8), ("msm_k", C.c_uint64 * 8),
+        ("msm_z", C.c_uint64 * 8), ("msm_b2", C.c_uint64 * 16), ("bs1", C.c_uint64 * 8),
+    ]
+
+    def as_dict(self):
+        return {name: np.array(getattr(self, name)[:], dtype=np.uint64) for name, _ in self._fields_}
 
 
 class Bases:
@@ -268,6 +296,62 @@ class Context:
             _ptr(indexes), height, n, _ptr(er) if er is not None else None, _ptr(roots),
             _ptr(ok) if ok is not None else None))
         return roots, (ok.astype(bool) if ok is not None else None)
+
+    # -- Groth16 prove (pk resident; mirrors groth16_bn254.Prove after Solve)
+    def pk_upload(self, log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2,
+                  infinity_a, infinity_b, k_skip):
+        """A/B/K/Z/B2: numpy point arrays (host) or Bases (already resident, borrowed)."""
+        keep = []                      # keep numpy buffers alive for the duration of the call
+
+        def vec(v, cols):
+            if isinstance(v, Bases):
+                return None, v.handle, v.n
+            a = _u64(v, cols)
+            keep.append(a)
+            return _ptr(a), None, a.shape[0]
+
+        d = PkDesc()
+        d.log2_domain, d.n_wires = log2_domain, n_wires
+        d.g1_a, d.res_a, d.n_a = vec(A, 8)
+        d.g1_b, d.res_b, d.n_b = vec(B, 8)
+        d.g1_k, d.res_k, d.n_k = vec(K, 8)
+        d.g1_z, d.res_z, d.n_z = vec(Z, 8)
+        d.g2_b, d.res_b2, nb2 = vec(B2, 16)
+        if nb2 != d.n_b:
+            raise B200Error("pk_upload: len(G2.B) != len(G1.B)")
+        for name, val, w in (("g1_alpha", alpha, 8), ("g1_beta", beta, 8), ("g1_delta", delta, 8),
+                             ("g2_beta", beta2, 16), ("g2_delta", delta2, 16)):
+            a = _u64(val).reshape(w)
+            keep.append(a)
+            setattr(d, name, _ptr(a))
+        for name, val in (("infinity_a", infinity_a), ("infinity_b", infinity_b), ("k_skip", k_skip)):
+            a = np.ascontiguousarray(val, dtype=np.uint8)
+            if a.shape[0] != n_wires:
+                raise B200Error(f"pk_upload: {name} must have n_wires entries")
+            keep.append(a)
+            setattr(d, name, _ptr(a))
+        h = _vp()
+        _check(load().b200g16_pk_upload(self.h, C.byref(d), C.byref(h)))
+        return h
+
+    def pk_free(self, pk):
+        load().b200g16_pk_free(pk)
+
+    def prove(self, pk, wires, a, b, c, r, s, want_h=False, log2_domain=None):
+        wires, a, b, c = _u64(wires, 4), _u64(a, 4), _u64(b, 4), _u64(c, 4)
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        out = ProofOut()
+        h = np.zeros((1 << log2_domain, 4), dtype=np.uint64) if want_h else None
+        _check(load().b200g16_prove(self.h, pk, _ptr(wires), wires.shape[0], _ptr(a), _ptr(b), _ptr(c), a.shape[0],
+                                    _ptr(r), _ptr(s), C.byref(out), _ptr(h) if want_h else None))
+        return out.as_dict(), h
+
+    def prove_dev(self, pk, d_wires, d_a, d_b, d_c, r, s):
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        out = ProofOut()
+        _check(load().b200g16_prove_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)),
+                                        _ptr(r), _ptr(s), C.byref(out)))
+        return out.as_dict()
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
     def msm(self, bases, scalars, offset=0, n=None):

@@ -46,6 +46,52 @@ extern "C" {
 
 typedef struct b200g16_ctx b200g16_ctx;
 typedef struct b200g16_bases b200g16_bases;
+typedef struct b200g16_pk b200g16_pk;
+
+/* groth16_bn254.ProvingKey as the prover needs it (gnark backend/groth16/bn254/setup.go).
+ * Each point vector is given EITHER as a host pointer (copied to the GPU once, owned by
+ * the pk handle) OR as an already-resident b200g16_bases (res_*, borrowed, must outlive
+ * the pk).  Lengths follow gnark: len(G1.A) = nbWires - NbInfinityA, len(G1.B) = len(G2.B)
+ * = nbWires - NbInfinityB, len(G1.K) = private non-committed wires, len(G1.Z) = N - 1
+ * (already bit-reversed by Setup). */
+typedef struct b200g16_pk_desc {
+  unsigned log2_domain;            /* pk.Domain.Cardinality = 2^log2_domain            */
+  size_t n_wires;                  /* len(witness vector) = len(pk.InfinityA)           */
+  const uint64_t* g1_a;            /* pk.G1.A   n_a x G1Affine                          */
+  const uint64_t* g1_b;            /* pk.G1.B   n_b x G1Affine                          */
+  const uint64_t* g1_k;            /* pk.G1.K   n_k x G1Affine                          */
+  const uint64_t* g1_z;            /* pk.G1.Z   n_z x G1Affine                          */
+  const uint64_t* g2_b;            /* pk.G2.B   n_b x G2Affine                          */
+  const b200g16_bases* res_a;      /* resident alternatives (NULL = use host pointer)   */
+  const b200g16_bases* res_b;
+  const b200g16_bases* res_k;
+  const b200g16_bases* res_z;
+  const b200g16_bases* res_b2;
+  size_t n_a, n_b, n_k, n_z;
+  const uint64_t* g1_alpha;        /* pk.G1.Alpha, Beta, Delta : G1Affine               */
+  const uint64_t* g1_beta;
+  const uint64_t* g1_delta;
+  const uint64_t* g2_beta;         /* pk.G2.Beta, Delta : G2Affine                      */
+  const uint64_t* g2_delta;
+  const uint8_t* infinity_a;       /* pk.InfinityA[n_wires] (1 = wire dropped from A)   */
+  const uint8_t* infinity_b;       /* pk.InfinityB[n_wires]                             */
+  const uint8_t* k_skip;           /* [n_wires] 1 = wire not in the K MSM: public wires,
+                                      BSB22-committed wires and commitment wires        */
+} b200g16_pk_desc;
+
+/* Proof{Ar, Bs, Krs} plus every intermediate MSM output, for parity checks against the
+ * CPU prover ("every intermediate MSM output ... must match", BASELINE.json north_star). */
+typedef struct b200g16_proof {
+  uint64_t ar[8];      /* proof.Ar                                  */
+  uint64_t bs[16];     /* proof.Bs  (G2)                            */
+  uint64_t krs[8];     /* proof.Krs                                 */
+  uint64_t msm_a[8];   /* MultiExp(pk.G1.A, wireValuesA)            */
+  uint64_t msm_b1[8];  /* MultiExp(pk.G1.B, wireValuesB)            */
+  uint64_t msm_k[8];   /* MultiExp(pk.G1.K, private wires)          */
+  uint64_t msm_z[8];   /* MultiExp(pk.G1.Z, h[:N-1])   (krs2)       */
+  uint64_t msm_b2[16]; /* MultiExp(pk.G2.B, wireValuesB)            */
+  uint64_t bs1[8];     /* bs1 = msm_b1 + beta + s*delta             */
+} b200g16_proof;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
 int b200g16_version(void);
@@ -166,6 +212,26 @@ int b200g16_keccak_merkle_paths_dev(b200g16_ctx* ctx, const void* d_leaves, size
                                     const void* d_siblings, const void* d_auth_paths,
                                     const void* d_indexes, unsigned height, size_t n_paths,
                                     const void* d_expected_root, void* d_roots_out, void* d_ok_out);
+
+/* ---- Groth16 prove ------------------------------------------------------------------- */
+/* Upload a proving key (once; stays resident like the icicle backend's device pk). */
+int b200g16_pk_upload(b200g16_ctx* ctx, const b200g16_pk_desc* desc, b200g16_pk** out);
+void b200g16_pk_free(b200g16_pk* pk);
+/* Everything gnark's groth16_bn254.Prove does after r1cs.Solve (backend/groth16/bn254/
+ * prove.go; reference call site mt.go:496):
+ *   wires  : the full solved witness vector, n_wires fr.Elements (Montgomery), host
+ *   a,b,c  : solution.A/B/C = L.w, R.w, O.w per constraint, n_constraints each, host
+ *   r, s   : the two blinding scalars (fr.Element, Montgomery).  gnark samples them
+ *            internally; they are parameters here so proofs are reproducible bit for bit.
+ * proof_out receives Ar, Bs, Krs and the intermediate MSM results; h_out (may be NULL)
+ * receives computeH's output: 2^log2_domain fr.Elements, bit-reversed order. */
+int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires, size_t n_wires,
+                  const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
+                  const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out, uint64_t* h_out);
+/* Same with wires / a / b / c already in DEVICE memory (a, b, c zero-padded to N and
+ * clobbered; h is left in d_a). */
+int b200g16_prove_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_a, void* d_b,
+                      void* d_c, const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out);
 
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */

@@ -1,0 +1,110 @@
+"""GPU parity: groth16 Setup / Prove through the host mirror + C-ABI vs the oracle's restatement
+of gnark v0.11.0 (reference call sites mt.go:448,496,497).  With toxic waste and r, s fixed,
+every pk/vk element, every intermediate MSM output, H, and the final proof must be identical;
+the proof must verify under the oracle's independent pairing and equal the closed form."""
+import random
+
+import numpy as np
+import pytest
+
+from gnark_whir_b200 import groth16 as g16
+from oracle import bn254 as bn
+from oracle import groth16 as og
+from oracle.bn254 import R
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, nb_constraints, nb_public, with_commitment):
+    rng = random.Random(seed)
+    r1cs, w = og.synthetic_r1cs(nb_constraints, nb_public, rng, with_commitment=with_commitment)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    r, s = rng.randrange(R), rng.randrange(R)
+    return r1cs, w, tw, r, s
+
+
+@pytest.mark.parametrize("nb_constraints,nb_public,with_commitment",
+                         [(1, 1, False), (7, 2, False), (24, 3, False), (24, 3, True), (100, 5, True), (257, 9, False)])
+def test_setup_prove_match_oracle_and_verify(ctx, nb_constraints, nb_public, with_commitment):
+    r1cs, w, tw, r, s = _case(nb_constraints * 7 + nb_public, nb_constraints, nb_public, with_commitment)
+    opk, ovk = og.setup(r1cs, tw)
+    pk, vk = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        # ---- Setup parity: every element of pk / vk
+        assert pk.log2_domain == opk.domain.logn
+        assert np.array_equal(pk.G1_A, bn.g1_to_array(opk.A))
+        assert np.array_equal(pk.G1_B, bn.g1_to_array(opk.B))
+        assert np.array_equal(pk.G1_Z, bn.g1_to_array(opk.Z))
+        assert np.array_equal(pk.G1_K, bn.g1_to_array(opk.K))
+        assert np.array_equal(pk.G2_B, bn.g2_to_array(opk.B2))
+        assert np.array_equal(pk.G1_Alpha, bn.g1_to_array([opk.alpha1])[0])
+        assert np.array_equal(pk.G1_Beta, bn.g1_to_array([opk.beta1])[0])
+        assert np.array_equal(pk.G1_Delta, bn.g1_to_array([opk.delta1])[0])
+        assert np.array_equal(pk.G2_Beta, bn.g2_to_array([opk.beta2])[0])
+        assert np.array_equal(pk.G2_Delta, bn.g2_to_array([opk.delta2])[0])
+        assert list(pk.InfinityA.astype(bool)) == opk.infinity_a
+        assert list(pk.InfinityB.astype(bool)) == opk.infinity_b
+        assert np.array_equal(vk.G1_K, bn.g1_to_array(ovk.K))
+        assert np.array_equal(vk.G2_Gamma, bn.g2_to_array([ovk.gamma2])[0])
+        if with_commitment:
+            assert np.array_equal(pk.CommitmentKeys[0].Basis, bn.g1_to_array(opk.ped_basis))
+            assert np.array_equal(pk.CommitmentKeys[0].BasisExpSigma, bn.g1_to_array(opk.ped_basis_exp_sigma))
+            assert np.array_equal(vk.PedersenGSigmaNeg, bn.g2_to_array([ovk.ped_g_sigma_neg])[0])
+
+        # ---- Prove parity
+        ow = list(w)
+        ocom = og.finalize_witness(r1cs, opk, ow)
+
+        def resolve(wit):                      # stands in for the solver finishing after the hint
+            L, Rr, O = r1cs.constraints[-1]
+            wit[O[0][0]] = og.lc_eval(L, wit) * og.lc_eval(Rr, wit) % R
+        proof = g16.Prove(ctx, r1cs, pk, w, r=r, s=s, resolve=resolve if with_commitment else None, want_h=True)
+        assert proof.debug["witness"] == ow
+        oproof, aux = og.prove(r1cs, opk, ow, r, s, commitment=ocom)
+        n = opk.domain.n
+        assert np.array_equal(proof.debug["h"], bn.fr_to_mont_array(aux["h"]))
+        wa = [ow[i] for i in range(r1cs.nb_wires) if not opk.infinity_a[i]]
+        wb = [ow[i] for i in range(r1cs.nb_wires) if not opk.infinity_b[i]]
+        wk = [ow[i] for i in opk.k_wires]
+        assert np.array_equal(proof.debug["msm_a"], bn.g1_to_array([bn.g1_msm(opk.A, wa)])[0])
+        assert np.array_equal(proof.debug["msm_b1"], bn.g1_to_array([bn.g1_msm(opk.B, wb)])[0])
+        assert np.array_equal(proof.debug["msm_k"], bn.g1_to_array([bn.g1_msm(opk.K, wk)])[0])
+        assert np.array_equal(proof.debug["msm_z"], bn.g1_to_array([aux["krs2"]])[0])
+        assert np.array_equal(proof.debug["msm_b2"], bn.g2_to_array([bn.g2_msm(opk.B2, wb)])[0])
+        assert np.array_equal(proof.debug["bs1"], bn.g1_to_array([aux["bs1"]])[0])
+        assert np.array_equal(proof.Ar, bn.g1_to_array([oproof.Ar])[0])
+        assert np.array_equal(proof.Bs, bn.g2_to_array([oproof.Bs])[0])
+        assert np.array_equal(proof.Krs, bn.g1_to_array([oproof.Krs])[0])
+        if with_commitment:
+            assert np.array_equal(proof.Commitments[0], bn.g1_to_array([oproof.commitments[0]])[0])
+            assert np.array_equal(proof.CommitmentPok, bn.g1_to_array([oproof.commitment_pok])[0])
+
+        # ---- the GPU proof verifies (independent pairing) and equals the closed form
+        gp = og.Proof(bn.g1_from_array(proof.Ar)[0], bn.g2_from_array(proof.Bs)[0], bn.g1_from_array(proof.Krs)[0],
+                      [bn.g1_from_array(c)[0] for c in proof.Commitments],
+                      bn.g1_from_array(proof.CommitmentPok)[0] if with_commitment else None)
+        assert og.verify(gp, ovk, ow[:r1cs.nb_public])
+        assert og.closed_form_proof(r1cs, tw, ow, r, s, aux["h"]) == (gp.Ar, gp.Bs, gp.Krs)
+        bad = list(ow[:r1cs.nb_public])
+        if len(bad) > 1:
+            bad[1] = (bad[1] + 1) % R
+            assert not og.verify(gp, ovk, bad)
+    finally:
+        pk.free()
+
+
+def test_prove_rejects_mismatched_inputs(ctx):
+    from gnark_whir_b200 import lib
+    r1cs, w, tw, r, s = _case(3, 8, 2, False)
+    pk, _ = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        h = pk.device_handle(ctx)
+        a, b, c = g16.solve_abc(r1cs, w)
+        with pytest.raises(lib.B200Error):      # wrong witness length
+            ctx.prove(h, g16.fr_array(w[:-1]), g16.fr_array(a), g16.fr_array(b), g16.fr_array(c),
+                      g16.fr_array([r])[0], g16.fr_array([s])[0])
+        with pytest.raises(lib.B200Error):      # more constraints than the domain
+            big = g16.fr_array(a * 3)
+            ctx.prove(h, g16.fr_array(w), big, big, big, g16.fr_array([r])[0], g16.fr_array([s])[0])
+    finally:
+        pk.free()
