@@ -1,0 +1,234 @@
+"""CPU tests: pin the oracle (python big-int + C port) with first-principles known answers.
+
+The reference ships no tests or vectors (parity unpinned), so these are the pins:
+hashlib for Keccak, the DFT definition for the NTT, group laws / bilinearity for the curve,
+the polynomial identity for computeH, the pairing equation and the toxic-waste closed form for
+Groth16; the C port (used for large sizes and as the timed CPU baseline) must equal the python
+oracle bit for bit."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as bn
+from oracle import cport
+from oracle import groth16 as og
+from oracle import keccak as ok
+from oracle import ntt as ont
+from oracle.bn254 import P, R
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ------------------------------------------------------------------ curve / pairing
+def test_constants_and_generators():
+    assert P.bit_length() == 254 and R.bit_length() == 254
+    assert bn.g1_on_curve(bn.G1_GEN) and bn.g2_on_curve(bn.G2_GEN)
+    assert bn.g1_mul(bn.G1_GEN, R - 1) == bn.g1_neg(bn.G1_GEN)
+    assert bn._mul(bn._F1, bn.G1_GEN, R, mod=1 << 300) is None      # [r]G = infinity
+    assert bn._mul(bn._F2, bn.G2_GEN, R, mod=1 << 300) is None
+    assert pow(ont.ROOT_2_28, 1 << 28, R) == 1 and pow(ont.ROOT_2_28, 1 << 27, R) == R - 1
+    assert (-pow(R, -1, 1 << 64)) % (1 << 64) == 0xc2e1f593efffffff
+    assert (-pow(P, -1, 1 << 64)) % (1 << 64) == 0x87d20782e4866389
+
+
+def test_group_homomorphism(rng):
+    a, b = rng.randrange(R), rng.randrange(R)
+    assert bn.g1_add(bn.g1_mul(bn.G1_GEN, a), bn.g1_mul(bn.G1_GEN, b)) == bn.g1_mul(bn.G1_GEN, a + b)
+    assert bn.g2_add(bn.g2_mul(bn.G2_GEN, a), bn.g2_mul(bn.G2_GEN, b)) == bn.g2_mul(bn.G2_GEN, a + b)
+
+
+def test_pairing_bilinear_nondegenerate(rng):
+    a, b = rng.randrange(1, R), rng.randrange(1, R)
+    e0 = bn.pairing(bn.G1_GEN, bn.G2_GEN)
+    assert e0 != bn.F12_ONE and bn.f12_pow(e0, R) == bn.F12_ONE
+    assert bn.pairing(bn.g1_mul(bn.G1_GEN, a), bn.g2_mul(bn.G2_GEN, b)) == bn.f12_pow(e0, a * b % R)
+    assert bn.pairing_check([(bn.g1_mul(bn.G1_GEN, a), bn.G2_GEN), (bn.g1_neg(bn.G1_GEN), bn.g2_mul(bn.G2_GEN, a))])
+
+
+def test_msm_known_dlog(rng):
+    ks = [rng.randrange(R) for _ in range(40)]
+    ss = [rng.randrange(R) for _ in range(40)]
+    pts = bn.g1_batch_mul_gen(ks)
+    exp = bn.g1_mul(bn.G1_GEN, sum(k * s for k, s in zip(ks, ss)) % R)
+    assert bn.g1_msm(pts, ss) == exp == bn.g1_msm_naive(pts, ss)
+    p2 = bn.g2_batch_mul_gen(ks[:6])
+    assert bn.g2_msm(p2, ss[:6]) == bn.g2_mul(bn.G2_GEN, sum(k * s for k, s in zip(ks[:6], ss[:6])) % R)
+
+
+# ------------------------------------------------------------------ NTT / computeH
+@pytest.mark.parametrize("logn", [1, 3, 6])
+def test_ntt_definition(rng, logn):
+    n = 1 << logn
+    d = ont.Domain(n)
+    a = [rng.randrange(R) for _ in range(n)]
+    X = ont.dft_naive(a, d.gen)
+    b = list(a)
+    d.fft(b, ont.DIF)
+    assert all(b[i] == X[ont.bitrev(i, logn)] for i in range(n))
+    b = [a[ont.bitrev(i, logn)] for i in range(n)]
+    d.fft(b, ont.DIT)
+    assert b == X
+    ev = [sum(a[j] * pow(5 * pow(d.gen, k, R), j, R) for j in range(n)) % R for k in range(n)]
+    b = [a[ont.bitrev(i, logn)] for i in range(n)]
+    d.fft(b, ont.DIT, coset=True)
+    assert b == ev
+    b = list(ev)
+    d.fft_inverse(b, ont.DIF, coset=True)
+    assert [b[ont.bitrev(i, logn)] for i in range(n)] == a
+
+
+def test_compute_h_identity(rng):
+    n_c, logn = 50, 6
+    d = ont.Domain(n_c)
+    A = [rng.randrange(R) for _ in range(n_c)]
+    B = [rng.randrange(R) for _ in range(n_c)]
+    Cc = [x * y % R for x, y in zip(A, B)]
+    h = ont.compute_h(A, B, Cc, d)
+    hc = [h[ont.bitrev(i, logn)] for i in range(64)]
+    assert hc[63] == 0
+
+    def interp(ev, x):
+        co = list(ev) + [0] * (64 - len(ev))
+        d.fft_inverse(co, ont.DIF)
+        return sum(co[ont.bitrev(i, logn)] * pow(x, i, R) for i in range(64)) % R
+    x = rng.randrange(R)
+    lhs = (interp(A, x) * interp(B, x) - interp(Cc, x)) % R
+    assert lhs == sum(c * pow(x, i, R) for i, c in enumerate(hc)) * (pow(x, 64, R) - 1) % R
+
+
+# ------------------------------------------------------------------ Keccak
+def test_keccak_pinned_by_hashlib():
+    assert ok.keccak_f([0] * 25)[0] == 0xF1258F7940E1DDE7
+    for n in (0, 1, 135, 136, 137, 300):
+        m = os.urandom(n)
+        assert ok.sha3_like(m, 136, 0x06, 32) == hashlib.sha3_256(m).digest()
+        assert ok.sha3_like(m, 168, 0x1F, 400) == hashlib.shake_128(m).digest(400)
+
+
+def test_sponge_permute_counts_and_merkle():
+    s = ok.Sponge(); s.absorb(bytes(512)); s.squeeze(32)
+    assert s.n_permutes == 4                     # 512-byte leaf -> 4 permutes
+    s = ok.Sponge(); s.absorb(bytes(64)); s.squeeze(32)
+    assert s.n_permutes == 1
+    s = ok.Sponge(tag=b"\x01\x02"); assert s.state[136] == 1 and s.state[137] == 2
+    leaves = [os.urandom(96) for _ in range(8)]
+    lv = ok.build_merkle_tree(leaves)
+    for i in range(8):
+        sib, ap = ok.merkle_open(lv, i)
+        assert ok.merkle_root_from_path(leaves[i], sib, ap, i) == lv[-1][0]
+        assert ok.merkle_root_from_path(leaves[i], sib, ap, i ^ 1) != lv[-1][0]
+
+
+def test_keccak_golden_vectors():
+    """Committed fixtures (tests/golden/keccak_sponge.json, made by tools/make_golden.py)."""
+    with open(os.path.join(GOLDEN, "keccak_sponge.json")) as f:
+        g = json.load(f)
+    for case in g["sponge"]:
+        assert ok.sponge_hash(bytes.fromhex(case["in"]), case["out_len"]).hex() == case["out"]
+        assert cport.sponge(bytes.fromhex(case["in"]), case["out_len"]).hex() == case["out"]
+    for case in g["keccak_f"]:
+        assert ok.keccak_f(case["in"]) == case["out"]
+
+
+# ------------------------------------------------------------------ Groth16
+@pytest.mark.parametrize("with_commitment", [False, True])
+def test_groth16_verifies_and_matches_closed_form(with_commitment):
+    rng = random.Random(11 + with_commitment)
+    r1cs, w = og.synthetic_r1cs(20, 3, rng, with_commitment=with_commitment)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    pk, vk = og.setup(r1cs, tw)
+    com = og.finalize_witness(r1cs, pk, w)
+    assert og.is_satisfied(r1cs, w)
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof, aux = og.prove(r1cs, pk, w, r, s, commitment=com)
+    assert og.verify(proof, vk, w[:r1cs.nb_public])
+    assert og.closed_form_proof(r1cs, tw, w, r, s, aux["h"]) == (proof.Ar, proof.Bs, proof.Krs)
+    bad = list(w[:r1cs.nb_public]); bad[1] ^= 1
+    assert not og.verify(proof, vk, bad)
+
+
+def test_groth16_golden_proof():
+    """A committed proof (tests/golden/groth16_small.json) reproduces and verifies."""
+    with open(os.path.join(GOLDEN, "groth16_small.json")) as f:
+        g = json.load(f)
+    rng = random.Random(g["seed"])
+    r1cs, w = og.synthetic_r1cs(g["nb_constraints"], g["nb_public"], rng, with_commitment=False)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    pk, vk = og.setup(r1cs, tw)
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof, aux = og.prove(r1cs, pk, w, r, s)
+    assert [hex(v) for v in proof.Ar] == g["Ar"]
+    assert [hex(v) for c in proof.Bs for v in c] == g["Bs"]
+    assert [hex(v) for v in proof.Krs] == g["Krs"]
+    assert og.verify(proof, vk, w[:r1cs.nb_public])
+
+
+# ------------------------------------------------------------------ C port == python oracle
+def test_cport_msm_and_progression(rng):
+    k0, d = rng.randrange(R), rng.randrange(R)
+    n = 300
+    pts = cport.g1_progression(bn.fr_to_mont_array([k0]), bn.fr_to_mont_array([d]), n)
+    for i in (0, 1, 2, 150, 299):
+        assert bn.g1_from_array(pts[i])[0] == bn.g1_mul(bn.G1_GEN, (k0 + i * d) % R)
+    ss = [rng.randrange(R) for _ in range(n)]
+    ss[3], ss[4], ss[5] = 0, 1, R - 1
+    sc = bn.fr_to_mont_array(ss)
+    exp = bn.g1_mul(bn.G1_GEN, sum(s * (k0 + i * d) for i, s in enumerate(ss)) % R)
+    for th in (1, 4):
+        assert bn.g1_from_array(cport.msm_g1(pts, sc, th))[0] == exp
+    dot = cport.fr_dot_progression(sc, bn.fr_to_mont_array([k0]), bn.fr_to_mont_array([d]))
+    assert bn.g1_from_array(cport.g1_gen_mul(dot))[0] == exp
+    assert bn.fr_from_mont_array(cport.fr_dot(sc, sc))[0] == sum(s * s for s in ss) % R
+
+
+def test_cport_msm_edge_cases(rng):
+    ks = [rng.randrange(1, R) for _ in range(6)]
+    pts = bn.g1_batch_mul_gen(ks)
+    pts = pts + [None, pts[0], pts[0], bn.g1_neg(pts[1])]
+    ss = [0, 1, R - 1, 7, 7, 9, 5, 3, 3, 1]
+    assert bn.g1_from_array(cport.msm_g1(bn.g1_to_array(pts), bn.fr_to_mont_array(ss)))[0] == bn.g1_msm_naive(pts, ss)
+    assert not cport.msm_g1(np.zeros((0, 8), np.uint64), np.zeros((0, 4), np.uint64)).any()
+
+
+@pytest.mark.parametrize("logn", [0, 1, 4, 9])
+def test_cport_ntt_and_compute_h(rng, logn):
+    n = 1 << logn
+    a = [rng.randrange(R) for _ in range(n)]
+    d = ont.Domain(n)
+    for inverse in (False, True):
+        for coset in (False, True):
+            for dec in (ont.DIF, ont.DIT):
+                exp = list(a)
+                (d.fft_inverse if inverse else d.fft)(exp, dec, coset=coset)
+                got = cport.ntt(bn.fr_to_mont_array(a), inverse, coset, dec)
+                assert np.array_equal(got, bn.fr_to_mont_array(exp))
+    m = max(1, n - 3)
+    A, B = a[:m], [rng.randrange(R) for _ in range(m)]
+    Cc = [x * y % R for x, y in zip(A, B)]
+    exp = ont.compute_h(A, B, Cc, d)
+    got = cport.compute_h(bn.fr_to_mont_array(A), bn.fr_to_mont_array(B), bn.fr_to_mont_array(Cc), logn)
+    assert np.array_equal(got, bn.fr_to_mont_array(exp))
+
+
+def test_cport_keccak(rng):
+    st = np.array([[rng.randrange(1 << 64) for _ in range(25)] for _ in range(9)], dtype=np.uint64)
+    got = cport.keccak_f_batch(st)
+    for i in range(9):
+        assert [int(v) for v in got[i]] == ok.keccak_f([int(v) for v in st[i]])
+    for n_in, n_out in ((0, 32), (1, 1), (136, 32), (137, 200), (512, 32)):
+        m = os.urandom(n_in)
+        assert cport.sponge(m, n_out) == ok.sponge_hash(m, n_out)
+    height, leaf_len = 5, 64
+    leaves = [os.urandom(leaf_len) for _ in range(1 << height)]
+    lv = ok.build_merkle_tree(leaves)
+    idxs = [0, 3, 17, 31]
+    opened = [ok.merkle_open(lv, i) for i in idxs]
+    roots = cport.merkle_paths(np.stack([np.frombuffer(leaves[i], np.uint8) for i in idxs]),
+                               np.stack([np.frombuffer(o[0], np.uint8) for o in opened]),
+                               np.stack([np.frombuffer(b"".join(o[1]), np.uint8).reshape(height - 1, 32) for o in opened]),
+                               np.array(idxs, np.uint64))
+    assert all(bytes(r) == lv[-1][0] for r in roots)
