@@ -142,6 +142,12 @@ int b200g16_bases_from_scalars_g2(b200g16_ctx* ctx, const uint64_t base[16], con
 int b200g16_modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, double* modmul_per_s,
                          float* ms);
 
+/* Instruction-level probe: ops/s of one integer instruction class with 8 independent chains
+ * per thread.  mode 0 IMAD (mad.lo.u32), 1 IMAD.WIDE (mad.wide.u32), 2 IMAD.WIDE.X carry
+ * chains (mad.lo.cc/madc.hi.cc pairs, what the Montgomery multiplier issues), 3 IMAD.HI,
+ * 4 IADD3.X carry chains, 5 modes 2 and 4 interleaved (reports the wide-MAD rate). */
+int b200g16_pipe_probe(b200g16_ctx* ctx, int mode, int blocks_per_sm, int iters, double* ops_per_s, float* ms);
+
 /* ---- multi-scalar multiplication -------------------------------------------------- */
 /* out = sum_i scalars[i] * bases[offset + i], i < n.  Replaces gnark-crypto
  * ecc/bn254 (*G1Affine).MultiExp / (*G2Affine).MultiExp as called by gnark
