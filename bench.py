@@ -281,8 +281,8 @@ def msm_windows_for(n):
             W += 1
         return W
     best, bc = 4, 1e300
-    for c in range(4, 17):
-        cost = nw(c) * (n + 6.0 * (1 << (c - 1)))
+    for c in range(4, 18):
+        cost = nw(c) * (n + 8.0 * (1 << (c - 1)))
         if cost < bc:
             best, bc = c, cost
     return nw(best)

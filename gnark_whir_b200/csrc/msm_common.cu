@@ -26,12 +26,14 @@ int msm_num_windows(int c) {
 }
 
 int msm_pick_window(size_t n) {
-  // minimise W(c) * (n + k * 2^(c-1)): k models the serial running-sum cost of the bucket
-  // reduction relative to one mixed add in a full-occupancy accumulate.
+  // minimise W(c) * (n + k * 2^(c-1)): k models the running-sum cost of the bucket reduction
+  // relative to one mixed add in a full-occupancy accumulate.  k = 8 and c <= 17 reproduce the
+  // measured optimum on B200 (profiles/r01_probe4_window_sweep.log: c = 15 @2^20, 17 @2^22..2^24;
+  // c = 18..20 lose more in the reduction than they save in the accumulation).
   int best = 4;
   double best_cost = 1e300;
-  for (int c = 4; c <= 16; c++) {
-    double cost = (double)msm_num_windows(c) * ((double)n + 6.0 * (double)(1u << (c - 1)));
+  for (int c = 4; c <= 17; c++) {
+    double cost = (double)msm_num_windows(c) * ((double)n + 8.0 * (double)(1u << (c - 1)));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -71,44 +73,103 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
   }
 }
 
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t seg,
-                                                uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
-                                                uint32_t* __restrict__ task_off, uint32_t* __restrict__ totals) {
-  __shared__ uint32_t s1[1024], s2[1024];
-  uint32_t t = threadIdx.x;
-  uint32_t per = (nb + 1023) / 1024;
-  uint32_t lo = t * per, hi = lo + per < nb ? lo + per : nb;
-  if (lo > nb) lo = nb;
-  uint32_t a = 0, b = 0;
-  for (uint32_t i = lo; i < hi; i++) {
-    uint32_t cnt = counts[i];
-    a += cnt;
-    b += (cnt + seg - 1) / seg;
+// ---- exclusive scan of (count, #tasks) per bucket: tile sums -> scan of tile sums -> apply
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __restrict__ counts, uint32_t nb,
+                                                             uint32_t seg, uint2* __restrict__ tile_sums) {
+  __shared__ uint32_t wa[SCAN_THREADS / 32], wb[SCAN_THREADS / 32];
+  uint32_t base = blockIdx.x * SCAN_TILE, a = 0, b = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    uint32_t i = base + threadIdx.x + SCAN_THREADS * j;
+    if (i < nb) { uint32_t cnt = counts[i]; a += cnt; b += (cnt + seg - 1) / seg; }
   }
-  s1[t] = a;
-  s2[t] = b;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, off);
+    b += __shfl_down_sync(0xffffffffu, b, off);
+  }
+  if ((threadIdx.x & 31) == 0) { wa[threadIdx.x >> 5] = a; wb[threadIdx.x >> 5] = b; }
   __syncthreads();
-  for (uint32_t off = 1; off < 1024; off <<= 1) {
-    uint32_t x = 0, y = 0;
-    if (t >= off) { x = s1[t - off]; y = s2[t - off]; }
+  if (threadIdx.x == 0) {
+    uint32_t ta = 0, tb = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) { ta += wa[w]; tb += wb[w]; }
+    tile_sums[blockIdx.x] = make_uint2(ta, tb);
+  }
+}
+
+// single CTA: in-place exclusive scan of the tile sums (chunks of 1024 with a running carry)
+__global__ void __launch_bounds__(1024) k_scan_top(uint2* __restrict__ tile_sums, uint32_t ntiles,
+                                                    uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s1[1024], s2[1024];
+  uint32_t t = threadIdx.x, ca = 0, cb = 0;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    uint32_t i = base + t;
+    uint2 v = i < ntiles ? tile_sums[i] : make_uint2(0, 0);
+    s1[t] = v.x;
+    s2[t] = v.y;
     __syncthreads();
-    s1[t] += x;
-    s2[t] += y;
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+      uint32_t x = 0, y = 0;
+      if (t >= off) { x = s1[t - off]; y = s2[t - off]; }
+      __syncthreads();
+      s1[t] += x;
+      s2[t] += y;
+      __syncthreads();
+    }
+    if (i < ntiles) tile_sums[i] = make_uint2(ca + s1[t] - v.x, cb + s2[t] - v.y);
+    ca += s1[1023];
+    cb += s2[1023];
     __syncthreads();
   }
-  uint32_t ea = s1[t] - a, eb = s2[t] - b;
-  for (uint32_t i = lo; i < hi; i++) {
-    uint32_t cnt = counts[i];
-    offsets[i] = ea;
-    cursor[i] = ea;
-    task_off[i] = eb;
-    ea += cnt;
-    eb += (cnt + seg - 1) / seg;
+  if (t == 0) {
+    totals[0] = ca;  // entries
+    totals[1] = cb;  // tasks
+    totals[2] = 0;   // heavy-bucket counter
   }
-  if (t == 1023) {
-    totals[0] = s1[1023];
-    totals[1] = s2[1023];
-    totals[2] = 0;  // heavy-bucket counter
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ counts, uint32_t nb,
+                                                              uint32_t seg, const uint2* __restrict__ tile_sums,
+                                                              uint32_t* __restrict__ offsets,
+                                                              uint32_t* __restrict__ cursor,
+                                                              uint32_t* __restrict__ task_off) {
+  __shared__ uint32_t wa[SCAN_THREADS / 32], wb[SCAN_THREADS / 32];
+  const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t cnt[SCAN_ITEMS], a = 0, b = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    cnt[j] = first + j < nb ? counts[first + j] : 0;
+    a += cnt[j];
+    b += (cnt[j] + seg - 1) / seg;
+  }
+  // inclusive scan of the per-thread sums across the CTA
+  uint32_t ia = a, ib = b;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t x = __shfl_up_sync(0xffffffffu, ia, off), y = __shfl_up_sync(0xffffffffu, ib, off);
+    if (lane >= (uint32_t)off) { ia += x; ib += y; }
+  }
+  if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+  __syncthreads();
+  uint32_t pa = 0, pb = 0;
+  for (uint32_t w = 0; w < warp; w++) { pa += wa[w]; pb += wb[w]; }
+  const uint2 tile = tile_sums[blockIdx.x];
+  uint32_t ea = tile.x + pa + ia - a, eb = tile.y + pb + ib - b;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    if (first + j < nb) {
+      offsets[first + j] = ea;
+      cursor[first + j] = ea;
+      task_off[first + j] = eb;
+    }
+    ea += cnt[j];
+    eb += (cnt[j] + seg - 1) / seg;
   }
 }
 
@@ -138,18 +199,22 @@ __global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ coun
 
 int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
                    uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
-                   uint32_t* entries, uint32_t* task_bucket, int* ev) {
+                   uint32_t* entries, uint32_t* task_bucket, uint32_t* scan_scratch, int* ev) {
   cudaStream_t st = ctx->stream;
   auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
   mark();
   B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * sizeof(uint32_t), st));
   k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.nbw, digits, counts);
   mark();
-  k_scan<<<1, 1024, 0, st>>>(counts, cfg.nb, cfg.seg, offsets, cursor, task_off, totals);
+  const uint32_t ntiles = cdiv(cfg.nb, SCAN_TILE);
+  uint2* tile_sums = reinterpret_cast<uint2*>(scan_scratch);
+  k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, cfg.seg, tile_sums);
+  k_scan_top<<<1, 1024, 0, st>>>(tile_sums, ntiles, totals);
+  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, cfg.seg, tile_sums, offsets, cursor, task_off);
   k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.nbw, cursor, entries);
   k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, cfg.seg, task_bucket);
   mark();
-  ctx->launches += 4;
+  ctx->launches += 6;
   B200_CUDA(cudaGetLastError());
   return 0;
 }

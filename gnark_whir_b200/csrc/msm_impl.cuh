@@ -41,7 +41,7 @@ int msm_pick_window(size_t n);
 // digits + histogram + scan + scatter + task table on ctx->stream (4 kernels + 1 memset)
 int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
                    uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
-                   uint32_t* entries, uint32_t* task_bucket, int* ev);
+                   uint32_t* entries, uint32_t* task_bucket, uint32_t* scan_scratch, int* ev);
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -205,7 +205,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   // task segment: a few times the mean bucket load, so uniform scalars give ~1 task per bucket
   size_t mean = m_max / cfg.nb + 1;
   cfg.seg = (uint32_t)(mean * 4 < 64 ? 64 : (mean * 4 > 8192 ? 8192 : mean * 4));
-  cfg.ch = cfg.nbw < 32 ? cfg.nbw : 32;
+  cfg.ch = cfg.nbw < 32 ? cfg.nbw : (cfg.nbw >= (1u << 17) ? 64 : 32);
   cfg.nch = cfg.nbw / cfg.ch;
   size_t max_tasks = (size_t)cfg.nb + m_max / cfg.seg + 1;
 
@@ -213,7 +213,9 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
   B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
   B200_TRY(ws.counts.ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
-  B200_TRY(ws.misc.ensure(64 + (size_t)cfg.nb * sizeof(uint32_t)));   // totals[16] + heavy list
+  // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
+  const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
+  B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 2) * sizeof(uint2)));
   B200_TRY(ws.tasks.ensure(max_tasks * sizeof(uint32_t)));
   B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
   B200_TRY(ws.buckets.ensure((size_t)cfg.nb * sizeof(XYZZ<F>)));
@@ -246,7 +248,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   auto mark = [&]() { if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
 
   B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
-                          task_bucket, record_events ? &ev : nullptr));
+                          task_bucket, reinterpret_cast<uint32_t*>(ws.misc.as<char>() + scan_off),
+                          record_events ? &ev : nullptr));
   k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_bucket, offsets, counts, task_off,
                                                          totals, cfg.seg, partials);
   mark();
