@@ -382,9 +382,113 @@ def extras_single_gpu(ctx, st, args):
     return ex
 
 
+def run_prove_workload(args, rank, local_rank, world):
+    """--workload prove (BASELINE.json configs[4]): synthetic WHIR-verifier-shaped Groth16 prove with
+    N = 2^prove_logn constraints and as many wires, proving key sharded by point range over the
+    ranks.  Every rank runs computeH (replicated) and the five MSMs on its shard; the five partial
+    points are all-gathered over NCCL and the proof is finished on the host."""
+    import torch
+    import torch.distributed as dist
+
+    from gnark_whir_b200 import groth16 as g16
+    from gnark_whir_b200 import lib, sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = lib.Context(local_rank)
+    L = args.prove_logn
+    N = 1 << L
+    rs = np.random.Generator(np.random.PCG64(SEED + 31 * rank))
+    g1, g2 = g16.g1_point(g16.G1_GEN), g16.g2_point(g16.G2_GEN)
+    lens = {"a": N, "b": N, "k": N - 1, "z": N - 1}
+    spans = {k: sharded.shard_range(v, rank, world) for k, v in lens.items()}
+    vec = {k: ctx.fixed_base_mul(g1, rand_fr(rs, hi - lo), group=1, resident=True) for k, (lo, hi) in spans.items()}
+    b2 = ctx.fixed_base_mul(g2, rand_fr(rs, spans["b"][1] - spans["b"][0]), group=2, resident=True)
+    common = np.random.Generator(np.random.PCG64(SEED))          # identical on every rank
+    small = ctx.fixed_base_mul(g1, rand_fr(common, 3), group=1)
+    small2 = ctx.fixed_base_mul(g2, rand_fr(common, 2), group=2)
+    k_skip = np.zeros(N, dtype=np.uint8)
+    k_skip[0] = 1
+    pk = ctx.pk_upload(L, N, vec["a"], vec["b"], vec["k"], vec["z"], b2, small[0], small[1], small[2], small2[0],
+                       small2[1], np.zeros(N, np.uint8), np.zeros(N, np.uint8), k_skip, partial=world > 1,
+                       offsets=(spans["a"][0], spans["b"][0], spans["k"][0], spans["z"][0]))
+    gen = torch.Generator(device=dev).manual_seed(SEED)
+
+    def rnd(shape):
+        t = torch.randint(0, 1 << 62, shape, dtype=torch.int64, device=dev, generator=gen)
+        t[..., 3] &= (1 << 60) - 1
+        return t
+    u = torch.rand(N, device=dev, generator=gen)
+    wires = rnd((N, 4))
+    smallv = torch.randint(0, 256, (N,), dtype=torch.int64, device=dev, generator=gen)
+    tbl = torch.from_numpy(g16.fr_array(list(range(256))).view(np.int64)).to(dev)
+    m01, mb = u < 0.4, (u >= 0.4) & (u < 0.7)
+    wires[m01] = tbl[smallv[m01] & 1]
+    wires[mb] = tbl[smallv[mb]]
+    a, b, c = rnd((N, 4)), rnd((N, 4)), rnd((N, 4))
+    rr, ss = rand_fr(common, 1)[0], rand_fr(common, 1)[0]
+
+    def step():
+        aa, bb, cc = a.clone(), b.clone(), c.clone()        # computeH works in place
+        part = ctx.prove_dev(pk, wires.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
+        if world == 1:
+            return part
+        t = torch.from_numpy(sharded.pack_partials(part).view(np.int64).copy()).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        sums = sharded.sum_partials([o.cpu().numpy().view(np.uint64) for o in outs])
+        return ctx.prove_finish(pk, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], rr, ss)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.launch_count() - l0
+    ph = ctx.last_timings()
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, launches = float(mx[0].item()), int(t[1].item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "WHIR-verifier-shaped Groth16 prove latency", "value": round(ms, 3), "unit": "ms",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"synthetic Groth16 prove, 2^{L} constraints, {N} wires, witness 40% 0/1 / 30% bytes / "
+                                   f"30% uniform (SURVEY §8d config 1/5), inputs resident in HBM",
+                       "parallelism": f"pk point-range shards x{world}; computeH replicated; all_gather of 5 partial points"},
+            "gpu_launches": launches,
+            "phases_ms_rank0[h2d,gather,computeH,msmA,msmB1,msmK,msmZ,msmB2]": [round(x, 3) for x in ph],
+            "proof_krs_limb0": int(res["krs"][0])}))
+    ctx.pk_free(pk)
+    for v in list(vec.values()) + [b2]:
+        v.free()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--workload", default="msm", choices=["msm", "prove"],
+                    help="msm = the headline (BASELINE configs[1]); prove = sharded synthetic Groth16 prove (configs[4])")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -405,6 +509,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if args.workload == "prove":
+        run_prove_workload(args, rank, local_rank, world)
+        return
     ctx, out, st = run_b200(args, rank, local_rank, world)
     if rank == 0:
         finish_integer_roofline(ctx, out, st, args)

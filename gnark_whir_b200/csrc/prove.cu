@@ -36,6 +36,9 @@ struct b200g16_pk {
   // wire -> scalar-vector gather lists (device): A, B, K
   uint32_t* d_idx[3] = {nullptr, nullptr, nullptr};
   size_t n_idx[3] = {0, 0, 0};
+  size_t off_z = 0;     // this ctx holds Z[off_z, off_z + n_z)
+  size_t n_z = 0;
+  bool partial = false; // shard of a key: prove returns partial MSM sums only
 };
 
 namespace b200 {
@@ -70,17 +73,18 @@ static Affine<F> host_sum(std::initializer_list<Affine<F>> pts) {
   return acc.to_affine();
 }
 
-static int build_index(const uint8_t* skip, size_t n_wires, size_t expect, uint32_t** d_out, const char* what) {
+// wires kept by `skip` flags, restricted to entries [off, off + expect) of that list (a shard of the key)
+static int build_index(const uint8_t* skip, size_t n_wires, size_t off, size_t expect, bool partial, uint32_t** d_out,
+                       const char* what) {
   std::vector<uint32_t> idx;
-  idx.reserve(expect);
   for (size_t i = 0; i < n_wires; i++)
     if (!skip[i]) idx.push_back((uint32_t)i);
-  if (idx.size() != expect)
-    return fail(B200G16_ERR_ARG, "pk_upload: %s flags keep %zu wires but the point vector has %zu", what, idx.size(),
-                expect);
-  B200_CUDA(cudaMalloc(d_out, (idx.size() ? idx.size() : 1) * sizeof(uint32_t)));
-  if (!idx.empty())
-    B200_CUDA(cudaMemcpy(*d_out, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (partial ? (off + expect > idx.size()) : (off != 0 || idx.size() != expect))
+    return fail(B200G16_ERR_ARG, "pk_upload: %s flags keep %zu wires; the point vector covers [%zu, %zu)", what,
+                idx.size(), off, off + expect);
+  B200_CUDA(cudaMalloc(d_out, (expect ? expect : 1) * sizeof(uint32_t)));
+  if (expect)
+    B200_CUDA(cudaMemcpy(*d_out, idx.data() + off, expect * sizeof(uint32_t), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -124,7 +128,13 @@ static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out
     }
   }
   size_t N = (size_t)1 << d->log2_domain;
-  if (d->n_z + 1 != N) { pk_release(pk); return fail(B200G16_ERR_ARG, "pk_upload: len(Z)=%zu, want N-1=%zu", d->n_z, N - 1); }
+  pk->partial = d->partial != 0;
+  pk->off_z = d->off_z;
+  pk->n_z = d->n_z;
+  if (pk->partial ? (d->off_z + d->n_z + 1 > N) : (d->off_z != 0 || d->n_z + 1 != N)) {
+    pk_release(pk);
+    return fail(B200G16_ERR_ARG, "pk_upload: Z covers [%zu, %zu), domain has N-1=%zu", d->off_z, d->off_z + d->n_z, N - 1);
+  }
   memcpy(&pk->alpha, d->g1_alpha, sizeof(G1Affine));
   memcpy(&pk->beta, d->g1_beta, sizeof(G1Affine));
   memcpy(&pk->delta, d->g1_delta, sizeof(G1Affine));
@@ -134,14 +144,30 @@ static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out
   cudaSetDevice(ctx->device);
   const uint8_t* flags[3] = {d->infinity_a, d->infinity_b, d->k_skip};
   const size_t expect[3] = {d->n_a, d->n_b, d->n_k};
+  const size_t offs[3] = {d->off_a, d->off_b, d->off_k};
   const char* names[3] = {"InfinityA", "InfinityB", "k_skip"};
   for (int i = 0; i < 3; i++) {
-    int st = build_index(flags[i], d->n_wires, expect[i], &pk->d_idx[i], names[i]);
+    int st = build_index(flags[i], d->n_wires, offs[i], expect[i], pk->partial, &pk->d_idx[i], names[i]);
     if (st) { pk_release(pk); return st; }
     pk->n_idx[i] = expect[i];
   }
   *out = pk;
   return 0;
+}
+
+// Ar, Bs, Krs (and bs1) from the five complete MSM results.
+static void prove_finish_host(const b200g16_pk* pk, const G1Affine& A, const G1Affine& B1, const G1Affine& K,
+                              const G1Affine& Z, const G2Affine& B2, const Fr& r, const Fr& s, b200g16_proof* out) {
+  Fr kr = Fr::neg(Fr::mul(r, s));
+  G1Affine ar = host_sum<Fp>({A, pk->alpha, host_scalar_mul_aff<Fp>(pk->delta, r)});
+  G1Affine bs1 = host_sum<Fp>({B1, pk->beta, host_scalar_mul_aff<Fp>(pk->delta, s)});
+  G1Affine krs = host_sum<Fp>({K, Z, host_scalar_mul_aff<Fp>(pk->delta, kr), host_scalar_mul_aff<Fp>(ar, s),
+                               host_scalar_mul_aff<Fp>(bs1, r)});
+  G2Affine bs = host_sum<Fp2>({B2, pk->beta2, host_scalar_mul_aff<Fp2>(pk->delta2, s)});
+  memcpy(out->ar, &ar, 64);
+  memcpy(out->bs, &bs, 128);
+  memcpy(out->krs, &krs, 64);
+  memcpy(out->bs1, &bs1, 64);
 }
 
 // d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
@@ -166,14 +192,13 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
   mark();
   MsmCfg cfg[5];
-  const size_t N = (size_t)1 << pk->log2n;
   B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[0]->d_points, sv[0], pk->n_idx[0], 0, &cfg[0], false));
   mark();
   B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[1]->d_points, sv[1], pk->n_idx[1], 1, &cfg[1], false));
   mark();
   B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[2]->d_points, sv[2], pk->n_idx[2], 2, &cfg[2], false));
   mark();
-  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[3]->d_points, d_a, N - 1, 3, &cfg[3], false));
+  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[3]->d_points, d_a + pk->off_z, pk->n_z, 3, &cfg[3], false));
   mark();
   B200_TRY(msm_enqueue<Fp2>(ctx, (const G2Affine*)pk->vec[4]->d_points, sv[1], pk->n_idx[1], 4, &cfg[4], false));
   mark();
@@ -188,21 +213,15 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   B200_TRY(msm_collect<Fp>(ctx, 3, cfg[3], &Z));
   B200_TRY(msm_collect<Fp2>(ctx, 4, cfg[4], &B2));
 
-  Fr kr = Fr::neg(Fr::mul(r, s));
-  G1Affine ar = host_sum<Fp>({A, pk->alpha, host_scalar_mul_aff<Fp>(pk->delta, r)});
-  G1Affine bs1 = host_sum<Fp>({B1, pk->beta, host_scalar_mul_aff<Fp>(pk->delta, s)});
-  G1Affine krs = host_sum<Fp>({K, Z, host_scalar_mul_aff<Fp>(pk->delta, kr), host_scalar_mul_aff<Fp>(ar, s),
-                               host_scalar_mul_aff<Fp>(bs1, r)});
-  G2Affine bs = host_sum<Fp2>({B2, pk->beta2, host_scalar_mul_aff<Fp2>(pk->delta2, s)});
-  memcpy(out->ar, &ar, 64);
-  memcpy(out->bs, &bs, 128);
-  memcpy(out->krs, &krs, 64);
+  memset(out, 0, sizeof(*out));
+  if (!pk->partial) {
+    prove_finish_host(pk, A, B1, K, Z, B2, r, s, out);
+  }
   memcpy(out->msm_a, &A, 64);
   memcpy(out->msm_b1, &B1, 64);
   memcpy(out->msm_k, &K, 64);
   memcpy(out->msm_z, &Z, 64);
   memcpy(out->msm_b2, &B2, 128);
-  memcpy(out->bs1, &bs1, 64);
   return 0;
 }
 
@@ -248,6 +267,23 @@ int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires,
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   if (h_out) B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int b200g16_prove_finish(const b200g16_pk* pk, const uint64_t msm_a[8], const uint64_t msm_b1[8],
+                         const uint64_t msm_k[8], const uint64_t msm_z[8], const uint64_t msm_b2[16],
+                         const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out) {
+  if (!pk || !msm_a || !msm_b1 || !msm_k || !msm_z || !msm_b2 || !r || !s || !proof_out)
+    return fail(B200G16_ERR_ARG, "prove_finish: null");
+  G1Affine A, B1, K, Z;
+  G2Affine B2;
+  Fr fr_r, fr_s;
+  memcpy(&A, msm_a, 64); memcpy(&B1, msm_b1, 64); memcpy(&K, msm_k, 64); memcpy(&Z, msm_z, 64);
+  memcpy(&B2, msm_b2, 128); memcpy(&fr_r, r, 32); memcpy(&fr_s, s, 32);
+  memset(proof_out, 0, sizeof(*proof_out));
+  prove_finish_host(pk, A, B1, K, Z, B2, fr_r, fr_s, proof_out);
+  memcpy(proof_out->msm_a, msm_a, 64); memcpy(proof_out->msm_b1, msm_b1, 64); memcpy(proof_out->msm_k, msm_k, 64);
+  memcpy(proof_out->msm_z, msm_z, 64); memcpy(proof_out->msm_b2, msm_b2, 128);
   return 0;
 }
 

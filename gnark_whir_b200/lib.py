@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200g16_pk_free": (None, [_vp]),
     "b200g16_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "b200g16_prove_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200g16_prove_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -137,6 +138,7 @@ class PkDesc(C.Structure):
         ("n_a", _sz), ("n_b", _sz), ("n_k", _sz), ("n_z", _sz),
         ("g1_alpha", _vp), ("g1_beta", _vp), ("g1_delta", _vp), ("g2_beta", _vp), ("g2_delta", _vp),
         ("infinity_a", _vp), ("infinity_b", _vp), ("k_skip", _vp),
+        ("partial", C.c_int), ("off_a", _sz), ("off_b", _sz), ("off_k", _sz), ("off_z", _sz),
     ]
 
 
@@ -306,8 +308,10 @@ class Context:
 
     # -- Groth16 prove (pk resident; mirrors groth16_bn254.Prove after Solve)
     def pk_upload(self, log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2,
-                  infinity_a, infinity_b, k_skip):
-        """A/B/K/Z/B2: numpy point arrays (host) or Bases (already resident, borrowed)."""
+                  infinity_a, infinity_b, k_skip, partial=False, offsets=(0, 0, 0, 0)):
+        """A/B/K/Z/B2: numpy point arrays (host) or Bases (already resident, borrowed).
+        partial=True: the vectors are entries [off, off+len) of the full key vectors
+        (offsets = (off_a, off_b, off_k, off_z)); prove() then returns partial MSM sums."""
         keep = []                      # keep numpy buffers alive for the duration of the call
 
         def vec(v, cols):
@@ -319,6 +323,8 @@ class Context:
 
         d = PkDesc()
         d.log2_domain, d.n_wires = log2_domain, n_wires
+        d.partial = int(bool(partial))
+        d.off_a, d.off_b, d.off_k, d.off_z = [int(x) for x in offsets]
         d.g1_a, d.res_a, d.n_a = vec(A, 8)
         d.g1_b, d.res_b, d.n_b = vec(B, 8)
         d.g1_k, d.res_k, d.n_k = vec(K, 8)
@@ -352,6 +358,14 @@ class Context:
         _check(load().b200g16_prove(self.h, pk, _ptr(wires), wires.shape[0], _ptr(a), _ptr(b), _ptr(c), a.shape[0],
                                     _ptr(r), _ptr(s), C.byref(out), _ptr(h) if want_h else None))
         return out.as_dict(), h
+
+    def prove_finish(self, pk, msm_a, msm_b1, msm_k, msm_z, msm_b2, r, s):
+        """Final assembly from the five complete (summed over shards) MSM results."""
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        pts = [_u64(v).reshape(w) for v, w in ((msm_a, 8), (msm_b1, 8), (msm_k, 8), (msm_z, 8), (msm_b2, 16))]
+        out = ProofOut()
+        _check(load().b200g16_prove_finish(pk, *[_ptr(p) for p in pts], _ptr(r), _ptr(s), C.byref(out)))
+        return out.as_dict()
 
     def prove_dev(self, pk, d_wires, d_a, d_b, d_c, r, s):
         r, s = _u64(r).reshape(4), _u64(s).reshape(4)

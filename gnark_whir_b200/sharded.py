@@ -55,6 +55,55 @@ def exchange_and_combine(local_partial, group=1, device=None, pg=None):
     return combine_partials(parts, group)
 
 
+PROOF_PARTS = (("msm_a", 8), ("msm_b1", 8), ("msm_k", 8), ("msm_z", 8), ("msm_b2", 16))
+
+
+def upload_pk_shard(ctx, pk, rank, world):
+    """Upload this rank's point-range shard of a groth16.ProvingKey (host arrays) -> pk handle.
+    Every vector is cut with shard_range(len, rank, world); flags stay whole."""
+    spans = [shard_range(len(v), rank, world) for v in (pk.G1_A, pk.G1_B, pk.G1_K, pk.G1_Z)]
+    (a0, a1), (b0, b1), (k0, k1), (z0, z1) = spans
+    return ctx.pk_upload(pk.log2_domain, len(pk.InfinityA), pk.G1_A[a0:a1], pk.G1_B[b0:b1], pk.G1_K[k0:k1],
+                         pk.G1_Z[z0:z1], pk.G2_B[b0:b1], pk.G1_Alpha, pk.G1_Beta, pk.G1_Delta, pk.G2_Beta,
+                         pk.G2_Delta, pk.InfinityA, pk.InfinityB, pk.k_skip, partial=True,
+                         offsets=(a0, b0, k0, z0))
+
+
+def pack_partials(proof_dict):
+    return np.concatenate([np.asarray(proof_dict[k], dtype=np.uint64).reshape(w) for k, w in PROOF_PARTS])
+
+
+def sum_partials(packed_list):
+    """packed_list: per-rank 48-word vectors -> dict of the five complete MSM results."""
+    out = {}
+    o = 0
+    for k, w in PROOF_PARTS:
+        out[k] = combine_partials([p[o:o + w] for p in packed_list], 1 if w == 8 else 2)
+        o += w
+    return out
+
+
+def prove_sharded(ctx, pk_shard, wires, a, b, c, r, s, device=None, pg=None):
+    """One rank's part of a sharded Groth16 prove: every rank runs computeH (replicated) and the
+    five MSMs on its shard, the 5 partial points (384 B) are all-gathered, and every rank
+    finishes the proof on the host.  Returns the same dict as Context.prove."""
+    import torch
+    import torch.distributed as dist
+    part, _ = ctx.prove(pk_shard, wires, a, b, c, r, s)
+    packed = pack_partials(part)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(pg) > 1:
+        t = torch.from_numpy(packed.view(np.int64).copy())
+        if device is not None:
+            t = t.to(device)
+        outs = [torch.empty_like(t) for _ in range(dist.get_world_size(pg))]
+        dist.all_gather(outs, t, group=pg)
+        packed_list = [o.cpu().numpy().view(np.uint64) for o in outs]
+    else:
+        packed_list = [packed]
+    sums = sum_partials(packed_list)
+    return ctx.prove_finish(pk_shard, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], r, s)
+
+
 class ShardedBases:
     """This rank's slice of a point vector, resident on this rank's GPU."""
 

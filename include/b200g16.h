@@ -77,6 +77,12 @@ typedef struct b200g16_pk_desc {
   const uint8_t* infinity_b;       /* pk.InfinityB[n_wires]                             */
   const uint8_t* k_skip;           /* [n_wires] 1 = wire not in the K MSM: public wires,
                                       BSB22-committed wires and commitment wires        */
+  /* Sharding across GPUs (point-range shards, one ctx per GPU).  partial = 0: the vectors are
+   * the whole key and the offsets must be 0.  partial = 1: the A/B(=B2)/K/Z vectors given above
+   * hold entries [off_x, off_x + n_x) of the full key vectors; b200g16_prove then returns only
+   * the partial MSM sums (msm_*), to be added across GPUs and passed to b200g16_prove_finish. */
+  int partial;
+  size_t off_a, off_b, off_k, off_z;
 } b200g16_pk_desc;
 
 /* Proof{Ar, Bs, Krs} plus every intermediate MSM output, for parity checks against the
@@ -234,6 +240,12 @@ void b200g16_pk_free(b200g16_pk* pk);
 int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires, size_t n_wires,
                   const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
                   const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out, uint64_t* h_out);
+/* Final assembly from the five COMPLETE MSM results (the sums over all shards):
+ * Ar = A + alpha + r*delta, Bs1 = B1 + beta + s*delta, Bs = B2 + beta2 + s*delta2,
+ * Krs = K + Z - rs*delta + s*Ar + r*Bs1.  Host only; any shard's pk handle supplies alpha..delta2. */
+int b200g16_prove_finish(const b200g16_pk* pk, const uint64_t msm_a[8], const uint64_t msm_b1[8],
+                         const uint64_t msm_k[8], const uint64_t msm_z[8], const uint64_t msm_b2[16],
+                         const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out);
 /* Same with wires / a / b / c already in DEVICE memory (a, b, c zero-padded to N and
  * clobbered; h is left in d_a). */
 int b200g16_prove_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_a, void* d_b,

@@ -108,3 +108,40 @@ def test_prove_rejects_mismatched_inputs(ctx):
             ctx.prove(h, g16.fr_array(w), big, big, big, g16.fr_array([r])[0], g16.fr_array([s])[0])
     finally:
         pk.free()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_prove_equals_single_gpu_prove(ctx, world):
+    """Point-range shards of the proving key (config 5): the shards' partial MSM sums, added and
+    finished on the host, must give the identical proof.  The ranks are emulated one after the
+    other on this GPU (same library calls a multi-process run makes; the exchange itself is
+    covered over gloo in test_sharded_cpu.py and over NCCL by bench.py --gpus N)."""
+    from gnark_whir_b200 import sharded
+    r1cs, w, tw, r, s = _case(77, 60, 4, False)
+    pk, _ = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        a, b, c = g16.solve_abc(r1cs, w)
+        args = (g16.fr_array(w), g16.fr_array(a), g16.fr_array(b), g16.fr_array(c), g16.fr_array([r])[0], g16.fr_array([s])[0])
+        full, _ = ctx.prove(pk.device_handle(ctx), *args)
+        packed, shard0 = [], None
+        for rank in range(world):
+            h = sharded.upload_pk_shard(ctx, pk, rank, world)
+            part, _ = ctx.prove(h, *args)
+            assert not part["ar"].any()                     # a shard never claims a finished proof
+            packed.append(sharded.pack_partials(part))
+            if rank == 0:
+                shard0 = h
+            else:
+                ctx.pk_free(h)
+        sums = sharded.sum_partials(packed)
+        for k in ("msm_a", "msm_b1", "msm_k", "msm_z", "msm_b2"):
+            assert np.array_equal(sums[k], full[k]), k
+        fin = ctx.prove_finish(shard0, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], args[4], args[5])
+        ctx.pk_free(shard0)
+        for k in ("ar", "bs", "krs", "bs1"):
+            assert np.array_equal(fin[k], full[k]), k
+        # world of one through the convenience wrapper
+        one = sharded.prove_sharded(ctx, sharded.upload_pk_shard(ctx, pk, 0, 1), *args)
+        assert np.array_equal(one["krs"], full["krs"])
+    finally:
+        pk.free()
