@@ -40,19 +40,28 @@ int msm_pick_window(size_t n) {
 }
 
 // ------------------------------------------------------------------------------ kernels
+// Window 0 is where small witness values (bits, bytes) pile up — 20% of a WHIR-verifier witness is
+// the scalar 1, i.e. one bucket — so its histogram / scatter atomics are warp-aggregated
+// (match.any: one atomic per distinct bucket per warp).  Other windows see near-uniform digits and
+// use plain atomics.
 __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, uint32_t n, int c, int W,
                                                  uint32_t nbw, int32_t* __restrict__ digits,
-                                                 uint32_t* __restrict__ counts) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = Fr::from_mont(scalars[i]);
+                                                 uint32_t* __restrict__ counts, uint32_t* __restrict__ totals) {
+  __shared__ uint32_t s_nz[8];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const bool valid = i < n;
   uint32_t limbs[9];
 #pragma unroll
-  for (int k = 0; k < 8; k++) limbs[k] = s.l[k];
-  limbs[8] = 0;
+  for (int k = 0; k < 9; k++) limbs[k] = 0;
+  if (valid) {
+    Fr s = Fr::from_mont(scalars[i]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) limbs[k] = s.l[k];
+  }
   const uint32_t mask = (c == 32) ? 0xffffffffu : ((1u << c) - 1u);
   const uint32_t half = 1u << (c - 1);
-  uint32_t carry = 0;
+  uint32_t carry = 0, nz = 0;
   for (int w = 0; w < W; w++) {
     int bit = w * c;
     int q = bit >> 5, r = bit & 31;
@@ -65,12 +74,40 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
     int32_t d;
     if (raw >= half) { d = (int32_t)raw - (int32_t)(1u << c); carry = 1; }
     else { d = (int32_t)raw; carry = 0; }
-    digits[(size_t)w * n + i] = d;
-    if (d != 0) {
-      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    if (valid) digits[(size_t)w * n + i] = d;
+    const bool hit = d != 0;
+    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    if (w == 0) {
+      const unsigned active = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const uint32_t key = mag - 1;
+        const unsigned peers = __match_any_sync(active, key);
+        if ((int)lane == __ffs(peers) - 1) atomicAdd(&counts[key], (uint32_t)__popc(peers));
+      }
+    } else if (hit) {
       atomicAdd(&counts[(uint32_t)w * nbw + mag - 1], 1u);
     }
+    nz += hit ? 1u : 0u;
   }
+  // number of (window, point) entries this launch produces -> totals[3] (drives the task size)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) nz += __shfl_down_sync(0xffffffffu, nz, off);
+  if (lane == 0) s_nz[threadIdx.x >> 5] = nz;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < 8; k++) t += s_nz[k];
+    if (t) atomicAdd(&totals[3], t);
+  }
+}
+
+// task size: large enough that evenly loaded buckets stay one task each, small enough that a skewed
+// input (few huge buckets) still yields >= target tasks.  totals[4] = seg.
+__global__ void k_pick_seg(uint32_t* __restrict__ totals, uint32_t nb, uint32_t target) {
+  uint32_t total = totals[3];
+  uint32_t a = 2u * (total / nb) + 2u, b = total / target + 1u;
+  uint32_t seg = a > b ? a : b;
+  totals[4] = seg < 32u ? 32u : seg;
 }
 
 // ---- exclusive scan of (count, #tasks) per bucket: tile sums -> scan of tile sums -> apply
@@ -79,8 +116,10 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(const uint32_t* __restrict__ counts, uint32_t nb,
-                                                             uint32_t seg, uint2* __restrict__ tile_sums) {
+                                                             const uint32_t* __restrict__ totals,
+                                                             uint2* __restrict__ tile_sums) {
   __shared__ uint32_t wa[SCAN_THREADS / 32], wb[SCAN_THREADS / 32];
+  const uint32_t seg = totals[4];
   uint32_t base = blockIdx.x * SCAN_TILE, a = 0, b = 0;
 #pragma unroll
   for (int j = 0; j < SCAN_ITEMS; j++) {
@@ -134,11 +173,13 @@ __global__ void __launch_bounds__(1024) k_scan_top(uint2* __restrict__ tile_sums
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ counts, uint32_t nb,
-                                                              uint32_t seg, const uint2* __restrict__ tile_sums,
+                                                              const uint32_t* __restrict__ totals,
+                                                              const uint2* __restrict__ tile_sums,
                                                               uint32_t* __restrict__ offsets,
                                                               uint32_t* __restrict__ cursor,
                                                               uint32_t* __restrict__ task_off) {
   __shared__ uint32_t wa[SCAN_THREADS / 32], wb[SCAN_THREADS / 32];
+  const uint32_t seg = totals[4];
   const uint32_t first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t cnt[SCAN_ITEMS], a = 0, b = 0;
 #pragma unroll
@@ -176,24 +217,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 // grid: (ceil(n/256), W) — window-major so that one window's scatter targets (4n bytes) live in L2
 __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ digits, uint32_t n, uint32_t nbw,
                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t w = blockIdx.y;
-  if (i >= n) return;
-  int32_t d = digits[(size_t)w * n + i];
-  if (d == 0) return;
-  uint32_t neg = d < 0;
-  uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-  uint32_t pos = atomicAdd(&cursor[w * nbw + mag - 1], 1u);
-  entries[pos] = (i << 1) | neg;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = blockIdx.y;
+  const uint32_t lane = threadIdx.x & 31;
+  const int32_t d = i < n ? digits[(size_t)w * n + i] : 0;
+  const bool hit = d != 0;
+  const uint32_t neg = d < 0;
+  const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
+  if (w == 0) {  // warp-aggregated: one atomic per distinct bucket per warp (see k_digits)
+    const unsigned active = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const uint32_t key = mag - 1;
+      const unsigned peers = __match_any_sync(active, key);
+      const int leader = __ffs(peers) - 1;
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      entries[base + rank] = (i << 1) | neg;
+    }
+  } else if (hit) {
+    uint32_t pos = atomicAdd(&cursor[w * nbw + mag - 1], 1u);
+    entries[pos] = (i << 1) | neg;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ task_off,
-                                                uint32_t nb, uint32_t seg, uint32_t* __restrict__ task_bucket) {
+                                                uint32_t nb, uint32_t* __restrict__ totals,
+                                                uint32_t* __restrict__ task_bucket) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  const uint32_t seg = totals[4];
   uint32_t nt = (counts[b] + seg - 1) / seg;
   uint32_t o = task_off[b];
   for (uint32_t t = 0; t < nt; t++) task_bucket[o + t] = b;
+  if (nt > 1) atomicMax(&totals[5], nt);  // deepest merge tree needed (k_merge_pass)
 }
 
 
@@ -204,17 +262,19 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
   mark();
   B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * sizeof(uint32_t), st));
-  k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.nbw, digits, counts);
+  B200_CUDA(cudaMemsetAsync(totals, 0, 16 * sizeof(uint32_t), st));
+  k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.nbw, digits, counts, totals);
+  k_pick_seg<<<1, 1, 0, st>>>(totals, cfg.nb, cfg.target_tasks);
   mark();
   const uint32_t ntiles = cdiv(cfg.nb, SCAN_TILE);
   uint2* tile_sums = reinterpret_cast<uint2*>(scan_scratch);
-  k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, cfg.seg, tile_sums);
+  k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums);
   k_scan_top<<<1, 1024, 0, st>>>(tile_sums, ntiles, totals);
-  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, cfg.seg, tile_sums, offsets, cursor, task_off);
+  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums, offsets, cursor, task_off);
   k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.nbw, cursor, entries);
-  k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, cfg.seg, task_bucket);
+  k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, totals, task_bucket);
   mark();
-  ctx->launches += 6;
+  ctx->launches += 7;
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -30,7 +30,7 @@ struct MsmCfg {
   int W;          // windows
   uint32_t nbw;   // buckets per window = 2^(c-1)
   uint32_t nb;    // W * nbw
-  uint32_t seg;   // max entries per accumulate task
+  uint32_t target_tasks;  // accumulate tasks wanted even for skewed inputs (device picks the task size)
   uint32_t ch;    // buckets per reduce chunk
   uint32_t nch;   // chunks per window
 };
@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict_
                                                      const uint32_t* __restrict__ offsets,
                                                      const uint32_t* __restrict__ counts,
                                                      const uint32_t* __restrict__ task_off,
-                                                     const uint32_t* __restrict__ totals, uint32_t seg,
+                                                     const uint32_t* __restrict__ totals,
                                                      XYZZ<F>* __restrict__ partials) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= totals[1]) return;
+  const uint32_t seg = totals[4];
   uint32_t b = task_bucket[t];
   uint32_t start = offsets[b] + (t - task_off[b]) * seg;
   uint32_t bend = offsets[b] + counts[b];
@@ -87,69 +88,50 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict_
   partials[t] = acc;
 }
 
-#define B200_MERGE_SERIAL_MAX 16u
+// Merge the partials of buckets that were split into several tasks: a fan-in-16 tree over the
+// (contiguous) partials of each bucket, one launch per level (stride = 16^level).  Thread t owns task
+// t; at a level only local indices that are multiples of 16*stride do work, reading slots no other
+// thread writes in the same launch.  After the last level the bucket's sum sits in its first partial.
+// totals[5] = largest #tasks of any bucket (written by k_tasks), so idle levels exit immediately.
+constexpr uint32_t MERGE_FANIN = 16;
 
 template <class F>
-__global__ void __launch_bounds__(128) k_merge(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ counts,
-                                                const uint32_t* __restrict__ task_off, uint32_t nb, uint32_t seg,
-                                                XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ totals,
-                                                uint32_t* __restrict__ heavy) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+__global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partials,
+                                                     const uint32_t* __restrict__ task_bucket,
+                                                     const uint32_t* __restrict__ counts,
+                                                     const uint32_t* __restrict__ task_off,
+                                                     const uint32_t* __restrict__ totals, uint32_t stride) {
+  if (stride >= totals[5]) return;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= totals[1]) return;
+  const uint32_t seg = totals[4];
+  uint32_t b = task_bucket[t];
   uint32_t nt = (counts[b] + seg - 1) / seg;
-  if (nt == 0) { buckets[b] = XYZZ<F>::inf(); return; }
-  uint32_t o = task_off[b];
-  if (nt > B200_MERGE_SERIAL_MAX) {
-    heavy[atomicAdd(&totals[2], 1u)] = b;
-    return;
+  uint32_t j = t - task_off[b];
+  if (stride >= nt || (j % (MERGE_FANIN * stride)) != 0) return;
+  XYZZ<F> acc = partials[t];
+  for (uint32_t q = 1; q < MERGE_FANIN; q++) {
+    uint32_t idx = j + q * stride;
+    if (idx >= nt) break;
+    acc.add(partials[t + q * stride]);
   }
-  XYZZ<F> acc = partials[o];
-  for (uint32_t t = 1; t < nt; t++) acc.add(partials[o + t]);
-  buckets[b] = acc;
-}
-
-template <class F>
-__global__ void __launch_bounds__(128) k_merge_heavy(const XYZZ<F>* __restrict__ partials,
-                                                      const uint32_t* __restrict__ counts,
-                                                      const uint32_t* __restrict__ task_off, uint32_t seg,
-                                                      XYZZ<F>* __restrict__ buckets,
-                                                      const uint32_t* __restrict__ totals,
-                                                      const uint32_t* __restrict__ heavy) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  uint32_t nheavy = totals[2];
-  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
-    uint32_t b = heavy[h];
-    uint32_t nt = (counts[b] + seg - 1) / seg;
-    uint32_t o = task_off[b];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t t = threadIdx.x; t < nt; t += blockDim.x) acc.add(partials[o + t]);
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-      if (threadIdx.x < s) {
-        acc.add(sm[threadIdx.x + s]);
-        sm[threadIdx.x] = acc;
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) buckets[b] = acc;
-    __syncthreads();
-  }
+  partials[t] = acc;
 }
 
 // thread per (window, chunk): sum_{b in chunk} (b+1) * B_b via a running sum from the top
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ buckets, int W, uint32_t nbw, uint32_t ch,
-                                                 uint32_t nch, int cbits, XYZZ<F>* __restrict__ chunks) {
+__global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ partials,
+                                                 const uint32_t* __restrict__ counts,
+                                                 const uint32_t* __restrict__ task_off, int W, uint32_t nbw,
+                                                 uint32_t ch, uint32_t nch, int cbits, XYZZ<F>* __restrict__ chunks) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (uint32_t)W * nch) return;
   uint32_t w = g / nch, k = g % nch;
   uint32_t lo = k * ch;
-  const XYZZ<F>* base = buckets + (size_t)w * nbw;
+  const uint32_t first = w * nbw + lo;  // bucket b's value = first partial of the bucket (after k_merge_pass)
   XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
   for (uint32_t j = ch; j-- > 0;) {
-    running.add(base[lo + j]);
+    if (counts[first + j]) running.add(partials[task_off[first + j]]);
     acc.add(running);
   }
   if (lo) {
@@ -202,12 +184,11 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   cfg.nb = cfg.nbw * (uint32_t)cfg.W;
   if ((double)n * cfg.W >= 4.0e9) return fail(B200G16_ERR_ARG, "msm: n*W overflows 32-bit entry index");
   size_t m_max = n * (size_t)cfg.W;
-  // task segment: a few times the mean bucket load, so uniform scalars give ~1 task per bucket
-  size_t mean = m_max / cfg.nb + 1;
-  cfg.seg = (uint32_t)(mean * 4 < 64 ? 64 : (mean * 4 > 8192 ? 8192 : mean * 4));
+  cfg.target_tasks = (uint32_t)ctx->sm_count * 2048u;  // ~4 waves of 512 resident threads per SM
   cfg.ch = cfg.nbw < 32 ? cfg.nbw : (cfg.nbw >= (1u << 17) ? 64 : 32);
   cfg.nch = cfg.nbw / cfg.ch;
-  size_t max_tasks = (size_t)cfg.nb + m_max / cfg.seg + 1;
+  // #tasks = sum ceil(cnt/seg) <= nb + total/seg <= nb + target (k_pick_seg keeps seg >= total/target)
+  size_t max_tasks = (size_t)cfg.nb + cfg.target_tasks + 64;
 
   MsmWorkspace& ws = ctx->msm;
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
@@ -218,7 +199,6 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 2) * sizeof(uint2)));
   B200_TRY(ws.tasks.ensure(max_tasks * sizeof(uint32_t)));
   B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
-  B200_TRY(ws.buckets.ensure((size_t)cfg.nb * sizeof(XYZZ<F>)));
   B200_TRY(ws.chunks.ensure((size_t)cfg.W * cfg.nch * sizeof(XYZZ<F>)));
   B200_TRY(ws.windows.ensure((size_t)cfg.W * sizeof(XYZZ<F>)));
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
@@ -234,12 +214,10 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   uint32_t* cursor = offsets + cfg.nb;
   uint32_t* task_off = cursor + cfg.nb;
   uint32_t* totals = ws.misc.as<uint32_t>();
-  uint32_t* heavy = totals + 16;
   int32_t* digits = ws.digits.as<int32_t>();
   uint32_t* entries = ws.entries.as<uint32_t>();
   uint32_t* task_bucket = ws.tasks.as<uint32_t>();
   XYZZ<F>* partials = ws.partials.as<XYZZ<F>>();
-  XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks.as<XYZZ<F>>();
   XYZZ<F>* windows = ws.windows.as<XYZZ<F>>();
   cudaStream_t st = ctx->stream;
@@ -251,17 +229,18 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
                           task_bucket, reinterpret_cast<uint32_t*>(ws.misc.as<char>() + scan_off),
                           record_events ? &ev : nullptr));
   k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_bucket, offsets, counts, task_off,
-                                                         totals, cfg.seg, partials);
+                                                         totals, partials);
   mark();
-  k_merge<F><<<cdiv(cfg.nb, 128), 128, 0, st>>>(partials, counts, task_off, cfg.nb, cfg.seg, buckets, totals, heavy);
-  k_merge_heavy<F><<<ctx->sm_count, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, counts, task_off, cfg.seg, buckets,
-                                                                       totals, heavy);
+  int merge_levels = 0;
+  for (uint64_t stride = 1; stride < max_tasks; stride *= MERGE_FANIN, merge_levels++)
+    k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(partials, task_bucket, counts, task_off, totals,
+                                                           (uint32_t)stride);
   mark();
-  k_reduce<F><<<cdiv((size_t)cfg.W * cfg.nch, 128), 128, 0, st>>>(buckets, cfg.W, cfg.nbw, cfg.ch, cfg.nch, cfg.c,
-                                                                   chunks);
+  k_reduce<F><<<cdiv((size_t)cfg.W * cfg.nch, 128), 128, 0, st>>>(partials, counts, task_off, cfg.W, cfg.nbw, cfg.ch,
+                                                                   cfg.nch, cfg.c, chunks);
   k_reduce2<F><<<cfg.W, 128, 128 * sizeof(XYZZ<F>), st>>>(chunks, cfg.nch, windows);
   mark();
-  ctx->launches += 5;
+  ctx->launches += 3 + merge_levels;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.W * sizeof(XYZZ<F>),
                             cudaMemcpyDeviceToHost, st));
