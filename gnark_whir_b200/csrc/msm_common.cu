@@ -255,9 +255,61 @@ __global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ coun
 }
 
 
+// ---- order tasks by length, longest first, so the 32 lanes of a warp run equal trip counts in
+// k_accumulate (bucket loads are Poisson distributed: without this the warp waits for its longest lane)
+constexpr uint32_t TASK_BINS = 4096;
+
+__device__ __forceinline__ uint32_t task_len(uint32_t cnt, uint32_t j, uint32_t seg) {
+  uint32_t rem = cnt - j * seg;
+  return rem < seg ? rem : seg;
+}
+
+__global__ void __launch_bounds__(256) k_task_hist(const uint32_t* __restrict__ task_bucket,
+                                                    const uint32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ task_off,
+                                                    const uint32_t* __restrict__ totals, uint32_t* __restrict__ hist) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= totals[1]) return;
+  uint32_t b = task_bucket[t];
+  uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
+  atomicAdd(&hist[len < TASK_BINS ? len : TASK_BINS - 1], 1u);
+}
+
+// single CTA, 1024 threads x 4 bins: exclusive scan in DESCENDING length order -> cursor[bin]
+__global__ void __launch_bounds__(1024) k_task_scan(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t s[1024];
+  uint32_t t = threadIdx.x, v[4], a = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = hist[TASK_BINS - 1 - (4 * t + k)]; a += v[k]; }
+  s[t] = a;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    uint32_t x = t >= off ? s[t - off] : 0;
+    __syncthreads();
+    s[t] += x;
+    __syncthreads();
+  }
+  uint32_t e = s[t] - a;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { cursor[TASK_BINS - 1 - (4 * t + k)] = e; e += v[k]; }
+}
+
+__global__ void __launch_bounds__(256) k_task_order(const uint32_t* __restrict__ task_bucket,
+                                                     const uint32_t* __restrict__ counts,
+                                                     const uint32_t* __restrict__ task_off,
+                                                     const uint32_t* __restrict__ totals, uint32_t* __restrict__ cursor,
+                                                     uint32_t* __restrict__ task_order) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= totals[1]) return;
+  uint32_t b = task_bucket[t];
+  uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
+  task_order[atomicAdd(&cursor[len < TASK_BINS ? len : TASK_BINS - 1], 1u)] = t;
+}
+
 int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
                    uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
-                   uint32_t* entries, uint32_t* task_bucket, uint32_t* scan_scratch, int* ev) {
+                   uint32_t* entries, uint32_t* task_bucket, uint32_t* task_order, uint32_t max_tasks,
+                   uint32_t* scan_scratch, int* ev) {
   cudaStream_t st = ctx->stream;
   auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
   mark();
@@ -268,13 +320,19 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   mark();
   const uint32_t ntiles = cdiv(cfg.nb, SCAN_TILE);
   uint2* tile_sums = reinterpret_cast<uint2*>(scan_scratch);
+  uint32_t* hist = scan_scratch + 2 * (size_t)(ntiles + 1);   // 2 x TASK_BINS words after the tile sums
+  uint32_t* hist_cursor = hist + TASK_BINS;
   k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums);
   k_scan_top<<<1, 1024, 0, st>>>(tile_sums, ntiles, totals);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums, offsets, cursor, task_off);
   k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.nbw, cursor, entries);
   k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, totals, task_bucket);
+  B200_CUDA(cudaMemsetAsync(hist, 0, TASK_BINS * sizeof(uint32_t), st));
+  k_task_hist<<<cdiv(max_tasks, 256), 256, 0, st>>>(task_bucket, counts, task_off, totals, hist);
+  k_task_scan<<<1, 1024, 0, st>>>(hist, hist_cursor);
+  k_task_order<<<cdiv(max_tasks, 256), 256, 0, st>>>(task_bucket, counts, task_off, totals, hist_cursor, task_order);
   mark();
-  ctx->launches += 7;
+  ctx->launches += 10;
   B200_CUDA(cudaGetLastError());
   return 0;
 }

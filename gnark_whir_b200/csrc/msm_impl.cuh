@@ -41,7 +41,8 @@ int msm_pick_window(size_t n);
 // digits + histogram + scan + scatter + task table on ctx->stream (4 kernels + 1 memset)
 int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
                    uint32_t* counts, uint32_t* offsets, uint32_t* cursor, uint32_t* task_off, uint32_t* totals,
-                   uint32_t* entries, uint32_t* task_bucket, uint32_t* scan_scratch, int* ev);
+                   uint32_t* entries, uint32_t* task_bucket, uint32_t* task_order, uint32_t max_tasks,
+                   uint32_t* scan_scratch, int* ev);
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -59,14 +60,16 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ bases,
                                                      const uint32_t* __restrict__ entries,
+                                                     const uint32_t* __restrict__ task_order,
                                                      const uint32_t* __restrict__ task_bucket,
                                                      const uint32_t* __restrict__ offsets,
                                                      const uint32_t* __restrict__ counts,
                                                      const uint32_t* __restrict__ task_off,
                                                      const uint32_t* __restrict__ totals,
                                                      XYZZ<F>* __restrict__ partials) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= totals[1]) return;
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= totals[1]) return;
+  const uint32_t t = task_order[gid];  // tasks sorted by length: the lanes of a warp finish together
   const uint32_t seg = totals[4];
   uint32_t b = task_bucket[t];
   uint32_t start = offsets[b] + (t - task_off[b]) * seg;
@@ -196,8 +199,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   B200_TRY(ws.counts.ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
   // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
   const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
-  B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 2) * sizeof(uint2)));
-  B200_TRY(ws.tasks.ensure(max_tasks * sizeof(uint32_t)));
+  B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
+  B200_TRY(ws.tasks.ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
   B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
   B200_TRY(ws.chunks.ensure((size_t)cfg.W * cfg.nch * sizeof(XYZZ<F>)));
   B200_TRY(ws.windows.ensure((size_t)cfg.W * sizeof(XYZZ<F>)));
@@ -217,6 +220,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   int32_t* digits = ws.digits.as<int32_t>();
   uint32_t* entries = ws.entries.as<uint32_t>();
   uint32_t* task_bucket = ws.tasks.as<uint32_t>();
+  uint32_t* task_order = task_bucket + max_tasks;
   XYZZ<F>* partials = ws.partials.as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks.as<XYZZ<F>>();
   XYZZ<F>* windows = ws.windows.as<XYZZ<F>>();
@@ -226,9 +230,10 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   auto mark = [&]() { if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
 
   B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
-                          task_bucket, reinterpret_cast<uint32_t*>(ws.misc.as<char>() + scan_off),
+                          task_bucket, task_order, (uint32_t)max_tasks,
+                          reinterpret_cast<uint32_t*>(ws.misc.as<char>() + scan_off),
                           record_events ? &ev : nullptr));
-  k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_bucket, offsets, counts, task_off,
+  k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_order, task_bucket, offsets, counts, task_off,
                                                          totals, partials);
   mark();
   int merge_levels = 0;
