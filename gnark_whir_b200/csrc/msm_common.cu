@@ -41,9 +41,10 @@ int msm_pick_window(size_t n) {
 
 // ------------------------------------------------------------------------------ kernels
 // Window 0 is where small witness values (bits, bytes) pile up — 20% of a WHIR-verifier witness is
-// the scalar 1, i.e. one bucket — so its histogram / scatter atomics are warp-aggregated
-// (match.any: one atomic per distinct bucket per warp).  Other windows see near-uniform digits and
-// use plain atomics.
+// the scalar 1, i.e. one bucket — and the top window may hold only a few scalar bits (2 bits at
+// c = 18), i.e. a handful of buckets; the histogram / scatter atomics of those two windows are
+// warp-aggregated (match.any: one atomic per distinct bucket per warp).  The windows in between
+// see near-uniform digits and use plain atomics.
 __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, uint32_t n, int c, int W,
                                                  uint32_t nbw, int32_t* __restrict__ digits,
                                                  uint32_t* __restrict__ counts, uint32_t* __restrict__ totals) {
@@ -77,10 +78,10 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
     if (valid) digits[(size_t)w * n + i] = d;
     const bool hit = d != 0;
     const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-    if (w == 0) {
+    if (w == 0 || w == W - 1) {
       const unsigned active = __ballot_sync(0xffffffffu, hit);
       if (hit) {
-        const uint32_t key = mag - 1;
+        const uint32_t key = (uint32_t)w * nbw + mag - 1;
         const unsigned peers = __match_any_sync(active, key);
         if ((int)lane == __ffs(peers) - 1) atomicAdd(&counts[key], (uint32_t)__popc(peers));
       }
@@ -224,10 +225,10 @@ __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ dig
   const bool hit = d != 0;
   const uint32_t neg = d < 0;
   const uint32_t mag = neg ? (uint32_t)(-d) : (uint32_t)d;
-  if (w == 0) {  // warp-aggregated: one atomic per distinct bucket per warp (see k_digits)
+  if (w == 0 || w == gridDim.y - 1) {  // warp-aggregated: one atomic per distinct bucket per warp (see k_digits)
     const unsigned active = __ballot_sync(0xffffffffu, hit);
     if (hit) {
-      const uint32_t key = mag - 1;
+      const uint32_t key = w * nbw + mag - 1;
       const unsigned peers = __match_any_sync(active, key);
       const int leader = __ffs(peers) - 1;
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));

@@ -1,0 +1,138 @@
+"""Config sweeps of BASELINE.json (run under gpurun): one JSON line per point -> stdout.
+
+  configs[1]  G1 MSM 2^16..2^24 (uniform + WHIR-shaped scalars), G2 MSM 2^16..2^22, each checked
+              against the closed form [sum s_i k_i]G computed by the C oracle
+  configs[2]  Fr NTT / computeH 2^18..2^26 (round-trip checked)
+  configs[3]  Keccak: raw 2^24 permutations, Merkle recompute for Q in {64,128,256} queries
+              (latency) and 2^20 independent paths (throughput), checked against the C oracle
+Timing: CUDA events on the library stream (b200g16_last_timings) or torch events around the call,
+best of 3 after one warm-up; inputs resident in HBM."""
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from gnark_whir_b200 import groth16 as g16  # noqa: E402
+from gnark_whir_b200 import lib  # noqa: E402
+from oracle import cport  # noqa: E402  (checker only)
+
+rs = np.random.Generator(np.random.PCG64(20261018))
+TMAD_PEAK = None
+
+
+def rand_fr(n):
+    a = rs.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def t_ms(fn, reps=3):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def main():
+    global TMAD_PEAK
+    big = "--big" in sys.argv
+    ctx = lib.Context(0)
+    rate, _ = ctx.modmul_probe(8, 4, 2000)
+    TMAD_PEAK = rate * 136 / 1e12
+    emit(probe="modmul", Gmodmul_s=round(rate / 1e9, 2), TMAD_s=round(TMAD_PEAK, 3))
+    tbl = torch.from_numpy(g16.fr_array(list(range(256))).view(np.int64)).cuda()
+
+    # ---- MSM sweeps
+    for group, logs in ((1, [16, 18, 20, 22, 24]), (2, [16, 18, 20, 22])):
+        gen = g16.g1_point(g16.G1_GEN) if group == 1 else g16.g2_point(g16.G2_GEN)
+        for logn in logs:
+            n = 1 << logn
+            ks = rand_fr(n)
+            bases = ctx.fixed_base_mul(gen, ks, group=group, resident=True)
+            sc = rand_fr(n)
+            d_uni = torch.from_numpy(sc.view(np.int64)).cuda()
+            u = torch.rand(n, device="cuda")
+            sv = torch.randint(0, 256, (n,), device="cuda")
+            d_mix = d_uni.clone()
+            m01, mb = u < 0.4, (u >= 0.4) & (u < 0.7)
+            d_mix[m01] = tbl[sv[m01] & 1]
+            d_mix[mb] = tbl[sv[mb]]
+            for name, d_sc in (("uniform", d_uni), ("whir_mix", d_mix)):
+                best, out = None, None
+                for _ in range(4):
+                    out = ctx.msm(bases, d_sc.data_ptr(), n=n)
+                    ph = ctx.last_timings()
+                    if best is None or sum(ph) < sum(best):
+                        best = ph
+                ok = None
+                if group == 1:
+                    host_sc = d_sc.cpu().numpy().view(np.uint64)
+                    ok = bool(np.array_equal(out, cport.g1_gen_mul(cport.fr_dot(ks, host_sc))))
+                ms = sum(best)
+                emit(config="msm", group=f"G{group}", log2n=logn, scalars=name, device_ms=round(ms, 3),
+                     Mpts_s=round(n / ms / 1e3, 2), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
+            bases.free()
+            del d_uni, d_mix
+
+    # ---- NTT / computeH sweeps
+    for logn in ([18, 20, 22, 24, 26] if big else [18, 20, 22, 24]):
+        n = 1 << logn
+        a = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+        ref = a.clone()
+        ctx.ntt_dev(a.data_ptr(), logn, coset=True, decimation=lib.DIF)
+        ctx.ntt_dev(a.data_ptr(), logn, inverse=True, coset=True, decimation=lib.DIT)
+        roundtrip = bool(torch.equal(a, ref))
+        ms = t_ms(lambda: ctx.ntt_dev(a.data_ptr(), logn, decimation=lib.DIF))
+        tmad = (n / 2) * logn * 136 / ms / 1e9
+        emit(config="ntt", log2n=logn, ms=round(ms, 4), GBs_64N=round(64 * n / ms / 1e6, 1), TMAD_s=round(tmad, 3),
+             frac_integer_peak=round(tmad / TMAD_PEAK, 3), roundtrip_exact=roundtrip)
+        b, c = torch.from_numpy(rand_fr(n).view(np.int64)).cuda(), torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+        ms = t_ms(lambda: ctx.compute_h_dev(a.data_ptr(), b.data_ptr(), c.data_ptr(), logn))
+        emit(config="compute_h", log2n=logn, ms=round(ms, 4), GBs_576N=round(576 * n / ms / 1e6, 1),
+             phases_ms=[round(x, 4) for x in ctx.last_timings()])
+        del a, b, c, ref
+
+    # ---- Keccak
+    nk = 1 << 24
+    st = torch.randint(0, 1 << 62, (nk, 25), dtype=torch.int64, device="cuda")
+    ms = t_ms(lambda: ctx.keccak_f_batch_dev(st.data_ptr(), nk))
+    emit(config="keccak_f_batch", states=nk, ms=round(ms, 4), Gperm_s=round(nk / ms / 1e6, 3), GBs_400B=round(400 * nk / ms / 1e6, 1))
+    del st
+    from ctypes import c_void_p
+    L = lib.load()
+    height, leaf_len = 20, 512
+    for q in (64, 128, 256, 1 << 20):
+        leaves = torch.randint(0, 256, (q, leaf_len), dtype=torch.uint8, device="cuda")
+        sib = torch.randint(0, 256, (q, 32), dtype=torch.uint8, device="cuda")
+        auth = torch.randint(0, 256, (q, height - 1, 32), dtype=torch.uint8, device="cuda")
+        idx = torch.randint(0, 1 << 20, (q,), dtype=torch.int64, device="cuda")
+        roots = torch.zeros((q, 32), dtype=torch.uint8, device="cuda")
+
+        def run():
+            lib._check(L.b200g16_keccak_merkle_paths_dev(ctx.h, c_void_p(leaves.data_ptr()), leaf_len,
+                                                         c_void_p(sib.data_ptr()), c_void_p(auth.data_ptr()),
+                                                         c_void_p(idx.data_ptr()), height, q, None,
+                                                         c_void_p(roots.data_ptr()), None))
+        ms = t_ms(run)
+        m = min(q, 512)
+        exp = cport.merkle_paths(leaves[:m].cpu().numpy(), sib[:m].cpu().numpy(), auth[:m].cpu().numpy(),
+                                 idx[:m].cpu().numpy().astype(np.uint64))
+        ok = bool(np.array_equal(roots[:m].cpu().numpy(), exp))
+        emit(config="keccak_merkle_paths", paths=q, height=height, leaf_len=leaf_len, ms=round(ms, 4),
+             Mpaths_s=round(q / ms / 1e3, 3), Gperm_s=round(24 * q / ms / 1e6, 4), byte_exact_vs_oracle=ok)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
