@@ -22,16 +22,16 @@ struct alignas(16) Fp2 {
   static B200_HD Fp2 dbl(const Fp2& a) { return {Fp::dbl(a.c0), Fp::dbl(a.c1)}; }
   static B200_HD Fp2 neg(const Fp2& a) { return {Fp::neg(a.c0), Fp::neg(a.c1)}; }
   // Karatsuba: 3 base-field products
-  static B200_HD_NOINLINE Fp2 mul(const Fp2& a, const Fp2& b) {
-    Fp t0 = Fp::mul(a.c0, b.c0);
-    Fp t1 = Fp::mul(a.c1, b.c1);
-    Fp t2 = Fp::mul(Fp::add(a.c0, a.c1), Fp::add(b.c0, b.c1));
+  static B200_HD Fp2 mul(const Fp2& a, const Fp2& b) {
+    Fp t0 = Fp::mul_call(a.c0, b.c0);
+    Fp t1 = Fp::mul_call(a.c1, b.c1);
+    Fp t2 = Fp::mul_call(Fp::add(a.c0, a.c1), Fp::add(b.c0, b.c1));
     return {Fp::sub(t0, t1), Fp::sub(Fp::sub(t2, t0), t1)};
   }
   // (a0+a1)(a0-a1) + 2 a0 a1 u : 2 products
-  static B200_HD_NOINLINE Fp2 sqr(const Fp2& a) {
-    Fp t0 = Fp::mul(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1));
-    Fp t1 = Fp::mul(a.c0, a.c1);
+  static B200_HD Fp2 sqr(const Fp2& a) {
+    Fp t0 = Fp::mul_call(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1));
+    Fp t1 = Fp::mul_call(a.c0, a.c1);
     return {t0, Fp::dbl(t1)};
   }
   static B200_HD Fp2 inv(const Fp2& a) {

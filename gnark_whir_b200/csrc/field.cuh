@@ -236,6 +236,15 @@ struct alignas(16) Field {
   }
   static B200_HD Field sqr(const Field& a) { return mul(a, a); }
 
+  // Out-of-line product, operands and result by value (registers): one copy of the multiplier
+  // shared by every call site.  Used by Fp2 so that the G2 kernels stay small and keep their
+  // register count (and therefore occupancy) close to the G1 kernels'.
+#if defined(__CUDACC__)
+  static __host__ __device__ __noinline__ Field mul_call(Field a, Field b) { return mul(a, b); }
+#else
+  static inline Field mul_call(Field a, Field b) { return mul(a, b); }
+#endif
+
   // x*R^-1 (Montgomery -> canonical) and x*R (canonical -> Montgomery)
   static B200_HD Field from_mont(const Field& a) {
     Field o = zero();

@@ -57,8 +57,10 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p
   return r;
 }
 
+// G1: 128 registers -> 4 CTAs/SM.  G2 (Fp2 coordinates): 220 registers, 2 CTAs/SM (capping it at 168
+// for 3 CTAs/SM spills and measures the same, profiles/r01 notes).
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F>* __restrict__ bases,
+__global__ void __launch_bounds__(128, (sizeof(F) > 32) ? 2 : 4) k_accumulate(const Affine<F>* __restrict__ bases,
                                                      const uint32_t* __restrict__ entries,
                                                      const uint32_t* __restrict__ task_order,
                                                      const uint32_t* __restrict__ task_bucket,
