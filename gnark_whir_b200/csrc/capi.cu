@@ -5,7 +5,13 @@
 
 namespace b200 {
 template <class F>
-int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, Affine<F>* out);
+int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, const Fr* d_scalars, size_t n,
+               Affine<F>* out);
+template <class F>
+int msm_build_table(b200g16_ctx* ctx, Affine<F>* table, size_t n, int c, int W);
+int msm_pick_table_window(size_t n);
+int msm_num_windows(int c);
+int msm_pick_window(size_t n);
 
 template <class F>
 int fixed_base_mul_device(b200g16_ctx* ctx, const Affine<F>& base, const Fr* d_scalars, size_t n, Affine<F>* d_out);
@@ -71,7 +77,16 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     d_scalars = ctx->msm.scalars.as<Fr>();
   }
   Affine<F> res;
-  B200_TRY(msm_device<F>(ctx, reinterpret_cast<const Affine<F>*>(bases->d_points) + offset, d_scalars, n, &res));
+  MsmTable tab;
+  const MsmTable* tp = nullptr;
+  const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
+  if (bases->tab_c) {
+    tab.c = bases->tab_c; tab.W = bases->tab_W; tab.stride = (uint32_t)bases->n; tab.off = (uint32_t)offset;
+    tp = &tab;
+  } else {
+    pts += offset;
+  }
+  B200_TRY(msm_device<F>(ctx, pts, tp, d_scalars, n, &res));
   memcpy(out, &res, sizeof(res));
   return 0;
 }
@@ -94,6 +109,30 @@ static int upload(b200g16_ctx* ctx, const uint64_t* points, size_t n, int group,
     return fail(B200G16_ERR_CUDA, "bases_upload: %s", cudaGetErrorString(e));
   }
   *out = b;
+  return 0;
+}
+
+// grow a resident vector into a window table: W rows of n points, row k = 2^(c k) * row 0
+template <class F>
+static int precompute(b200g16_ctx* ctx, b200g16_bases* b, int c) {
+  const size_t n = b->n;
+  if (n == 0) return 0;
+  if (c == 0) c = msm_pick_table_window(n);
+  if (c < 8 || c > 22) return fail(B200G16_ERR_ARG, "bases_precompute: window %d outside [8, 22]", c);
+  const int W = msm_num_windows(c);
+  if ((double)n * W >= 2.0e9) return fail(B200G16_ERR_ARG, "bases_precompute: %zu x %d points exceed the entry index", n, W);
+  Affine<F>* table = nullptr;
+  cudaError_t e = cudaMalloc(&table, (size_t)W * n * sizeof(Affine<F>));
+  if (e != cudaSuccess)
+    return fail(B200G16_ERR_CUDA, "bases_precompute: %d rows of %zu points: %s", W, n, cudaGetErrorString(e));
+  e = cudaMemcpyAsync(table, b->d_points, n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, ctx->stream);
+  int st = e == cudaSuccess ? msm_build_table<F>(ctx, table, n, c, W)
+                            : fail(B200G16_ERR_CUDA, "bases_precompute: %s", cudaGetErrorString(e));
+  if (st) { cudaFree(table); return st; }
+  cudaFree(b->d_points);
+  b->d_points = table;
+  b->tab_c = c;
+  b->tab_W = W;
   return 0;
 }
 
@@ -199,6 +238,24 @@ void b200g16_bases_free(b200g16_bases* b) {
   delete b;
 }
 size_t b200g16_bases_len(const b200g16_bases* b) { return b ? b->n : 0; }
+
+int b200g16_bases_precompute(b200g16_ctx* ctx, b200g16_bases* b, int window_bits) {
+  if (!ctx || !b) return fail(B200G16_ERR_ARG, "bases_precompute: null");
+  if (b->device != ctx->device) return fail(B200G16_ERR_STATE, "bases_precompute: bases live on another device");
+  if (b->tab_c) return fail(B200G16_ERR_STATE, "bases_precompute: vector already carries a c=%d table", b->tab_c);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return b->group == 1 ? precompute<Fp>(ctx, b, window_bits) : precompute<Fp2>(ctx, b, window_bits);
+}
+int b200g16_bases_window(const b200g16_bases* b) { return b ? b->tab_c : 0; }
+
+int b200g16_msm_plan(const b200g16_ctx* ctx, const b200g16_bases* b, size_t n, int* window_bits, int* windows) {
+  if (!ctx || !b || !window_bits || !windows) return fail(B200G16_ERR_ARG, "msm_plan: null");
+  int c = b->tab_c ? b->tab_c : (ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(n));
+  *window_bits = c;
+  *windows = msm_num_windows(c);
+  return 0;
+}
 
 int b200g16_bases_download(const b200g16_bases* b, size_t offset, size_t n, uint64_t* out) {
   if (!b || !out) return fail(B200G16_ERR_ARG, "bases_download: null");

@@ -76,6 +76,13 @@ struct NttWorkspace {
   int coset_log = -1;  // coset tables built for exactly 2^coset_log
 };
 
+// descriptor of a window table attached to a bases vector (b200g16_bases_precompute)
+struct MsmTable {
+  int c, W;
+  uint32_t stride;  // points per row (= length of the bases vector)
+  uint32_t off;     // first point of the sub-range this MSM uses
+};
+
 struct Timings {
   // last-call device timings in ms (CUDA events on ctx stream); index = phase
   float ms[16];
@@ -101,6 +108,9 @@ struct b200g16_ctx {
 struct b200g16_bases {
   int group = 1;  // 1 = G1, 2 = G2
   size_t n = 0;
-  void* d_points = nullptr;
+  void* d_points = nullptr;  // n points; after b200g16_bases_precompute: tab_W rows of n points,
+                             // row k = 2^(tab_c * k) * P_i
   int device = 0;
+  int tab_c = 0;             // 0 = no window table
+  int tab_W = 0;
 };

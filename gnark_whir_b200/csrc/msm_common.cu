@@ -39,6 +39,18 @@ int msm_pick_window(size_t n) {
   return best;
 }
 
+int msm_pick_table_window(size_t n) {
+  int best = 8;
+  double best_cost = 1e300;
+  for (int c = 8; c <= 22; c++) {
+    const int W = msm_num_windows(c);
+    if ((double)n * W >= 2.0e9) continue;
+    double cost = (double)W * (double)n + 24.0 * (double)(1u << (c - 1));
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
 // ------------------------------------------------------------------------------ kernels
 // Window 0 is where small witness values (bits, bytes) pile up — 20% of a WHIR-verifier witness is
 // the scalar 1, i.e. one bucket — and the top window may hold only a few scalar bits (2 bits at
@@ -46,7 +58,7 @@ int msm_pick_window(size_t n) {
 // warp-aggregated (match.any: one atomic per distinct bucket per warp).  The windows in between
 // see near-uniform digits and use plain atomics.
 __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, uint32_t n, int c, int W,
-                                                 uint32_t nbw, int32_t* __restrict__ digits,
+                                                 uint32_t bstride, int32_t* __restrict__ digits,
                                                  uint32_t* __restrict__ counts, uint32_t* __restrict__ totals) {
   __shared__ uint32_t s_nz[8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,12 +93,12 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
     if (w == 0 || w == W - 1) {
       const unsigned active = __ballot_sync(0xffffffffu, hit);
       if (hit) {
-        const uint32_t key = (uint32_t)w * nbw + mag - 1;
+        const uint32_t key = (uint32_t)w * bstride + mag - 1;
         const unsigned peers = __match_any_sync(active, key);
         if ((int)lane == __ffs(peers) - 1) atomicAdd(&counts[key], (uint32_t)__popc(peers));
       }
     } else if (hit) {
-      atomicAdd(&counts[(uint32_t)w * nbw + mag - 1], 1u);
+      atomicAdd(&counts[(uint32_t)w * bstride + mag - 1], 1u);
     }
     nz += hit ? 1u : 0u;
   }
@@ -102,12 +114,14 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
   }
 }
 
-// task size: large enough that evenly loaded buckets stay one task each, small enough that a skewed
-// input (few huge buckets) still yields >= target tasks.  totals[4] = seg.
+// task size.  Many buckets (nb >= target): evenly loaded buckets stay one task each (seg = 2 x mean),
+// and a skewed input (few huge buckets) still yields >= target tasks.  Few buckets (window tables with
+// a narrow window, small windows): the buckets are cut so that ~target tasks exist at all — otherwise
+// the accumulate kernel would run with a fraction of the SMs' threads.  totals[4] = seg.
 __global__ void k_pick_seg(uint32_t* __restrict__ totals, uint32_t nb, uint32_t target) {
   uint32_t total = totals[3];
   uint32_t a = 2u * (total / nb) + 2u, b = total / target + 1u;
-  uint32_t seg = a > b ? a : b;
+  uint32_t seg = (nb >= target && a > b) ? a : b;
   totals[4] = seg < 32u ? 32u : seg;
 }
 
@@ -216,7 +230,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 }
 
 // grid: (ceil(n/256), W) — window-major so that one window's scatter targets (4n bytes) live in L2
-__global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ digits, uint32_t n, uint32_t nbw,
+// bstride: bucket-index stride between windows (2^(c-1), or 0 when all windows share one bucket set
+// because the bases carry a window table); entry = index into the (table of) bases
+// = w * ent_stride + ent_off + i.
+__global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ digits, uint32_t n, uint32_t bstride,
+                                                  uint32_t ent_stride, uint32_t ent_off,
                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t w = blockIdx.y;
@@ -228,18 +246,18 @@ __global__ void __launch_bounds__(256) k_scatter(const int32_t* __restrict__ dig
   if (w == 0 || w == gridDim.y - 1) {  // warp-aggregated: one atomic per distinct bucket per warp (see k_digits)
     const unsigned active = __ballot_sync(0xffffffffu, hit);
     if (hit) {
-      const uint32_t key = w * nbw + mag - 1;
+      const uint32_t key = w * bstride + mag - 1;
       const unsigned peers = __match_any_sync(active, key);
       const int leader = __ffs(peers) - 1;
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       uint32_t base = 0;
       if ((int)lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
       base = __shfl_sync(peers, base, leader);
-      entries[base + rank] = (i << 1) | neg;
+      entries[base + rank] = ((w * ent_stride + ent_off + i) << 1) | neg;
     }
   } else if (hit) {
-    uint32_t pos = atomicAdd(&cursor[w * nbw + mag - 1], 1u);
-    entries[pos] = (i << 1) | neg;
+    uint32_t pos = atomicAdd(&cursor[w * bstride + mag - 1], 1u);
+    entries[pos] = ((w * ent_stride + ent_off + i) << 1) | neg;
   }
 }
 
@@ -316,7 +334,7 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   mark();
   B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * sizeof(uint32_t), st));
   B200_CUDA(cudaMemsetAsync(totals, 0, 16 * sizeof(uint32_t), st));
-  k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.nbw, digits, counts, totals);
+  k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.bstride, digits, counts, totals);
   k_pick_seg<<<1, 1, 0, st>>>(totals, cfg.nb, cfg.target_tasks);
   mark();
   const uint32_t ntiles = cdiv(cfg.nb, SCAN_TILE);
@@ -326,7 +344,7 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums);
   k_scan_top<<<1, 1024, 0, st>>>(tile_sums, ntiles, totals);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums, offsets, cursor, task_off);
-  k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.nbw, cursor, entries);
+  k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.bstride, cfg.ent_stride, cfg.ent_off, cursor, entries);
   k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, totals, task_bucket);
   B200_CUDA(cudaMemsetAsync(hist, 0, TASK_BINS * sizeof(uint32_t), st));
   k_task_hist<<<cdiv(max_tasks, 256), 256, 0, st>>>(task_bucket, counts, task_off, totals, hist);

@@ -29,7 +29,11 @@ struct MsmCfg {
   int c;          // window bits
   int W;          // windows
   uint32_t nbw;   // buckets per window = 2^(c-1)
-  uint32_t nb;    // W * nbw
+  uint32_t nb;    // buckets in total: W * nbw, or nbw when the bases carry a window table
+  int Wr;         // window sums produced by the reduction: W, or 1 with a window table
+  uint32_t bstride;     // bucket-index stride between windows: nbw, or 0 with a window table
+  uint32_t ent_stride;  // entry = w * ent_stride + ent_off + i  (index into the bases / the table)
+  uint32_t ent_off;
   uint32_t target_tasks;  // accumulate tasks wanted even for skewed inputs (device picks the task size)
   uint32_t ch;    // buckets per reduce chunk
   uint32_t nch;   // chunks per window
@@ -146,47 +150,52 @@ __global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ part
   chunks[g] = acc;
 }
 
-// block per window: tree-sum the chunk results
+// plain sums, fan-in 16: out[w][g] = sum_{j<16} in[w][16 g + j]   (len_in items per window, thread per g);
+// applied until one item per window is left
+constexpr uint32_t SUM_FANIN = 16;
+
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce2(const XYZZ<F>* __restrict__ chunks, uint32_t nch,
-                                                  XYZZ<F>* __restrict__ windows) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  uint32_t w = blockIdx.x;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t k = threadIdx.x; k < nch; k += blockDim.x) acc.add(chunks[(size_t)w * nch + k]);
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      acc.add(sm[threadIdx.x + s]);
-      sm[threadIdx.x] = acc;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) windows[w] = acc;
+__global__ void __launch_bounds__(128) k_sum_pass(const XYZZ<F>* __restrict__ in, uint32_t len_in, uint32_t len_out,
+                                                   uint32_t total_out, XYZZ<F>* __restrict__ out) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_out) return;
+  uint32_t w = g / len_out, k = g % len_out;
+  const XYZZ<F>* src = in + (size_t)w * len_in;
+  uint32_t lo = k * SUM_FANIN, hi = lo + SUM_FANIN < len_in ? lo + SUM_FANIN : len_in;
+  XYZZ<F> acc = src[lo];
+  for (uint32_t j = lo + 1; j < hi; j++) acc.add(src[j]);
+  out[g] = acc;
 }
 
 // ------------------------------------------------------------------------------ host driver
+// Window table attached to a bases vector (b200g16_bases_precompute): row k holds 2^(c k) * P_i, so
+// digit k of scalar i addresses entry k * stride + i and ALL windows accumulate into one bucket set.
+// (struct MsmTable lives in common.cuh)
 constexpr int MSM_SLOTS = 8;           // independent result slots (a prove enqueues 5 MSMs back to back)
 constexpr int MSM_MAX_WINDOWS = 130;
 
 // Enqueue one MSM on ctx->stream; its W window sums land in pinned slot `slot` once the stream
 // drains.  No host synchronisation.  record_events: fill ctx->ev for b200g16_last_timings.
 template <class F>
-int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, int slot, MsmCfg* cfg_out,
-                bool record_events) {
+int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, const Fr* d_scalars, size_t n, int slot,
+                MsmCfg* cfg_out, bool record_events) {
   MsmCfg cfg;
   memset(&cfg, 0, sizeof(cfg));
   *cfg_out = cfg;
   if (slot < 0 || slot >= MSM_SLOTS) return fail(B200G16_ERR_ARG, "msm: bad slot");
   if (n == 0) return 0;  // cfg.W == 0 marks "infinity"
   if (n >= (1ull << 31)) return fail(B200G16_ERR_ARG, "msm: n=%zu too large", n);
-  cfg.c = ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(n);
+  cfg.c = tab ? tab->c : (ctx->msm_window_override ? ctx->msm_window_override : msm_pick_window(n));
   if (cfg.c < 2 || cfg.c > 24) return fail(B200G16_ERR_ARG, "msm: window %d out of range", cfg.c);
   cfg.W = msm_num_windows(cfg.c);
+  if (tab && tab->W != cfg.W) return fail(B200G16_ERR_STATE, "msm: window table has %d rows, want %d", tab->W, cfg.W);
   cfg.nbw = 1u << (cfg.c - 1);
-  cfg.nb = cfg.nbw * (uint32_t)cfg.W;
+  cfg.Wr = tab ? 1 : cfg.W;
+  cfg.nb = cfg.nbw * (uint32_t)cfg.Wr;
+  cfg.bstride = tab ? 0u : cfg.nbw;
+  cfg.ent_stride = tab ? tab->stride : 0u;
+  cfg.ent_off = tab ? tab->off : 0u;
+  if (tab && (double)tab->stride * cfg.W >= 2.0e9) return fail(B200G16_ERR_ARG, "msm: window table too large to index");
   if ((double)n * cfg.W >= 4.0e9) return fail(B200G16_ERR_ARG, "msm: n*W overflows 32-bit entry index");
   size_t m_max = n * (size_t)cfg.W;
   cfg.target_tasks = (uint32_t)ctx->sm_count * 2048u;  // ~4 waves of 512 resident threads per SM
@@ -204,8 +213,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
   B200_TRY(ws.tasks.ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
   B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
-  B200_TRY(ws.chunks.ensure((size_t)cfg.W * cfg.nch * sizeof(XYZZ<F>)));
-  B200_TRY(ws.windows.ensure((size_t)cfg.W * sizeof(XYZZ<F>)));
+  B200_TRY(ws.chunks.ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
   if (ws.pinned_cap < MSM_SLOTS * slot_bytes) {
     if (ws.pinned) cudaFreeHost(ws.pinned);
@@ -225,7 +233,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
   uint32_t* task_order = task_bucket + max_tasks;
   XYZZ<F>* partials = ws.partials.as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks.as<XYZZ<F>>();
-  XYZZ<F>* windows = ws.windows.as<XYZZ<F>>();
+  XYZZ<F>* windows = nullptr;
   cudaStream_t st = ctx->stream;
   uint32_t n32 = (uint32_t)n;
   int ev = 0;
@@ -243,13 +251,23 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars,
     k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(partials, task_bucket, counts, task_off, totals,
                                                            (uint32_t)stride);
   mark();
-  k_reduce<F><<<cdiv((size_t)cfg.W * cfg.nch, 128), 128, 0, st>>>(partials, counts, task_off, cfg.W, cfg.nbw, cfg.ch,
-                                                                   cfg.nch, cfg.c, chunks);
-  k_reduce2<F><<<cfg.W, 128, 128 * sizeof(XYZZ<F>), st>>>(chunks, cfg.nch, windows);
+  k_reduce<F><<<cdiv((size_t)cfg.Wr * cfg.nch, 128), 128, 0, st>>>(partials, counts, task_off, cfg.Wr, cfg.nbw, cfg.ch,
+                                                                    cfg.nch, cfg.c, chunks);
+  // chunk sums -> one sum per window: ping-pong between the two halves of the chunk buffer
+  XYZZ<F>* cur = chunks;
+  XYZZ<F>* nxt = chunks + (size_t)cfg.Wr * cfg.nch;
+  int sum_levels = 0;
+  for (uint32_t len = cfg.nch; len > 1; sum_levels++) {
+    const uint32_t len_out = (len + SUM_FANIN - 1) / SUM_FANIN, total_out = (uint32_t)cfg.Wr * len_out;
+    k_sum_pass<F><<<cdiv(total_out, 128), 128, 0, st>>>(cur, len, len_out, total_out, nxt);
+    XYZZ<F>* t = cur; cur = nxt; nxt = t;
+    len = len_out;
+  }
+  windows = cur;  // Wr items
   mark();
-  ctx->launches += 3 + merge_levels;
+  ctx->launches += 2 + merge_levels + sum_levels;
   B200_CUDA(cudaGetLastError());
-  B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.W * sizeof(XYZZ<F>),
+  B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.Wr * sizeof(XYZZ<F>),
                             cudaMemcpyDeviceToHost, st));
   if (record_events) ctx->timings.n = -(ev - 1);  // negative: events recorded, not yet resolved
   *cfg_out = cfg;
@@ -263,8 +281,8 @@ int msm_collect(b200g16_ctx* ctx, int slot, const MsmCfg& cfg, Affine<F>* out) {
   if (cfg.W == 0) { *out = Affine<F>::inf(); return 0; }
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
   const XYZZ<F>* hw = reinterpret_cast<const XYZZ<F>*>((const char*)ctx->msm.pinned + (size_t)slot * slot_bytes);
-  XYZZ<F> acc = hw[cfg.W - 1];
-  for (int w = cfg.W - 2; w >= 0; w--) {
+  XYZZ<F> acc = hw[cfg.Wr - 1];
+  for (int w = cfg.Wr - 2; w >= 0; w--) {
     for (int k = 0; k < cfg.c; k++) acc.dbl();
     acc.add(hw[w]);
   }
@@ -280,13 +298,87 @@ inline void msm_resolve_timings(b200g16_ctx* ctx) {
 }
 
 template <class F>
-int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const Fr* d_scalars, size_t n, Affine<F>* out) {
+int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, const Fr* d_scalars, size_t n,
+               Affine<F>* out) {
   MsmCfg cfg;
   ctx->timings.n = 0;
-  B200_TRY(msm_enqueue<F>(ctx, d_bases, d_scalars, n, 0, &cfg, true));
+  B200_TRY(msm_enqueue<F>(ctx, d_bases, tab, d_scalars, n, 0, &cfg, true));
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
   msm_resolve_timings(ctx);
   return msm_collect<F>(ctx, 0, cfg, out);
+}
+
+// ------------------------------------------------------------------------------ window tables
+// row[i] = 2^c * prev[i] in affine form.  Each thread owns TABLE_BATCH points (strided, so loads and
+// stores coalesce): c doublings each in XYZZ, then ONE field inversion shared by the batch
+// (Montgomery's trick) for the affine normal forms.
+constexpr int TABLE_BATCH = 4;
+
+template <class F>
+__global__ void __launch_bounds__(128) k_table_row(const Affine<F>* __restrict__ prev, Affine<F>* __restrict__ next,
+                                                    uint32_t n, int c) {
+  const uint32_t T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+  XYZZ<F> p[TABLE_BATCH];
+  F pref[TABLE_BATCH];
+  F acc = F::one();
+#pragma unroll 1
+  for (int k = 0; k < TABLE_BATCH; k++) {
+    const uint32_t i = t + (uint32_t)k * T;
+    XYZZ<F> q = XYZZ<F>::inf();
+    if (i < n) {
+      q = XYZZ<F>::from_affine(load_affine(prev + i));
+      for (int j = 0; j < c; j++) q.dbl();
+    }
+    pref[k] = acc;
+    if (!q.is_inf()) acc = F::mul(acc, q.zzz);
+    p[k] = q;
+  }
+  F inv = F::inv(acc);
+#pragma unroll 1
+  for (int k = TABLE_BATCH - 1; k >= 0; k--) {
+    const uint32_t i = t + (uint32_t)k * T;
+    if (i >= n) continue;
+    Affine<F> o = Affine<F>::inf();
+    if (!p[k].is_inf()) {
+      F zi = F::mul(inv, pref[k]);  // 1 / zzz_k
+      inv = F::mul(inv, p[k].zzz);
+      F izz = F::sqr(F::mul(p[k].zz, zi));  // 1 / zz_k = (zz/zzz)^2
+      o.x = F::mul(p[k].x, izz);
+      o.y = F::mul(p[k].y, zi);
+    }
+    next[i] = o;
+  }
+}
+
+// Window width for a table over n bases: minimise W(c) * n (accumulate adds) + 8 * 2^(c-1) (ONE
+// bucket set to reduce, same cost model as msm_pick_window), subject to the 31-bit entry index.
+int msm_pick_table_window(size_t n);
+
+// table: W rows of n points, row 0 already holds the bases.
+template <class F>
+int msm_build_table(b200g16_ctx* ctx, Affine<F>* table, size_t n, int c, int W) {
+  if (n == 0) return 0;
+  const unsigned grid = cdiv(cdiv(n, TABLE_BATCH), 128);
+  for (int k = 1; k < W; k++) {
+    k_table_row<F><<<grid, 128, 0, ctx->stream>>>(table + (size_t)(k - 1) * n, table + (size_t)k * n, (uint32_t)n, c);
+    ctx->launches++;
+  }
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// (bases pointer, table descriptor) for points [offset, offset + n) of a resident vector
+template <class F>
+inline const Affine<F>* msm_operand(const b200g16_bases* b, size_t offset, MsmTable* tab, const MsmTable** tab_out) {
+  const Affine<F>* p = reinterpret_cast<const Affine<F>*>(b->d_points);
+  if (b->tab_c) {
+    tab->c = b->tab_c; tab->W = b->tab_W; tab->stride = (uint32_t)b->n; tab->off = (uint32_t)offset;
+    *tab_out = tab;
+    return p;
+  }
+  *tab_out = nullptr;
+  return p + offset;
 }
 
 }  // namespace b200

@@ -18,9 +18,9 @@
 namespace b200 {
 int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
 // instantiated in msm_g1.cu / msm_g2.cu
-extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
 extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
-extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
 extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
 }  // namespace b200
 
@@ -125,6 +125,10 @@ static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out
                         : b200g16_bases_upload_g1(ctx, host[i], n[i], &pk->vec[i]);
       if (st) { pk_release(pk); return st; }
       pk->owned[i] = true;
+      if (d->precompute && n[i]) {
+        st = b200g16_bases_precompute(ctx, pk->vec[i], 0);
+        if (st) { pk_release(pk); return st; }
+      }
     }
   }
   size_t N = (size_t)1 << d->log2_domain;
@@ -192,16 +196,20 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
   mark();
   MsmCfg cfg[5];
-  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[0]->d_points, sv[0], pk->n_idx[0], 0, &cfg[0], false));
-  mark();
-  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[1]->d_points, sv[1], pk->n_idx[1], 1, &cfg[1], false));
-  mark();
-  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[2]->d_points, sv[2], pk->n_idx[2], 2, &cfg[2], false));
-  mark();
-  B200_TRY(msm_enqueue<Fp>(ctx, (const G1Affine*)pk->vec[3]->d_points, d_a + pk->off_z, pk->n_z, 3, &cfg[3], false));
-  mark();
-  B200_TRY(msm_enqueue<Fp2>(ctx, (const G2Affine*)pk->vec[4]->d_points, sv[1], pk->n_idx[1], 4, &cfg[4], false));
-  mark();
+  const Fr* scal[5] = {sv[0], sv[1], sv[2], d_a + pk->off_z, sv[1]};
+  const size_t cnt[5] = {pk->n_idx[0], pk->n_idx[1], pk->n_idx[2], pk->n_z, pk->n_idx[1]};
+  for (int i = 0; i < 5; i++) {
+    MsmTable tab;
+    const MsmTable* tp = nullptr;
+    if (i < 4) {
+      const G1Affine* pts = msm_operand<Fp>(pk->vec[i], 0, &tab, &tp);
+      B200_TRY(msm_enqueue<Fp>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
+    } else {
+      const G2Affine* pts = msm_operand<Fp2>(pk->vec[i], 0, &tab, &tp);
+      B200_TRY(msm_enqueue<Fp2>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
+    }
+    mark();
+  }
   B200_CUDA(cudaStreamSynchronize(st));
   *ev_io = ev;
 

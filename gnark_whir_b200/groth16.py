@@ -120,11 +120,14 @@ class ProvingKey:                  # groth16_bn254.ProvingKey
     _dev: object = None            # device handle, filled lazily on first Prove (like gnark's icicle pk)
     _ctx: object = None
 
-    def device_handle(self, ctx):
+    def device_handle(self, ctx, precompute=False):
+        """precompute=True: attach window tables to the resident point vectors at upload time
+        (b200g16_bases_precompute) — more HBM, fewer additions per MSM, identical proofs."""
         if self._dev is None:
             self._dev = ctx.pk_upload(self.log2_domain, len(self.InfinityA), self.G1_A, self.G1_B, self.G1_K,
                                       self.G1_Z, self.G2_B, self.G1_Alpha, self.G1_Beta, self.G1_Delta,
-                                      self.G2_Beta, self.G2_Delta, self.InfinityA, self.InfinityB, self.k_skip)
+                                      self.G2_Beta, self.G2_Delta, self.InfinityA, self.InfinityB, self.k_skip,
+                                      precompute=precompute)
             self._ctx = ctx
         return self._dev
 
@@ -314,6 +317,23 @@ def Prove(ctx, r1cs, pk, witness, r=None, s=None, resolve=None, want_h=False):
     return Proof(out["ar"], out["krs"], out["bs"], proof_commitments, pok, dbg)
 
 
-def Verify(proof, vk, public_witness):
-    raise NotImplementedError("groth16.Verify on the B200 path is a later row (SURVEY §8f rank 3); "
-                              "tests check proofs with the oracle's independent pairing")
+def Verify(ctx, proof, vk, public_witness):
+    """groth16.Verify(proof, vk, publicWitness) -> None, raises on an invalid proof (gnark returns
+    an error).  public_witness: values of the public wires WITHOUT the constant-one wire, as in
+    gnark's witness.Public().  Runs b200g16_verify: the public-input MSM and the pairing product
+    on the GPU; only the BSB22 challenge hash (SHA-256 over ~100 bytes) is computed here."""
+    pub = [int(v) % R_MOD for v in public_witness]
+    com = pok = None
+    if vk.has_commitment:
+        if not proof.Commitments or proof.CommitmentPok is None:
+            raise ValueError("groth16.Verify: proof carries no commitment but the circuit has one")
+        com, pok = proof.Commitments[0], proof.CommitmentPok
+        # PublicAndCommitmentCommitted holds wire indexes (wire 0 = the constant one)
+        committed = [1 if i == 0 else pub[i - 1] for i in vk.PublicAndCommitmentCommitted]
+        pub.append(commitment_challenge(com, committed))
+    ok = ctx.verify(vk.G1_Alpha, vk.G2_Beta, vk.G2_Gamma, vk.G2_Delta, vk.G1_K, proof.Ar, proof.Bs, proof.Krs,
+                    fr_array(pub) if pub else np.zeros((0, 4), dtype=np.uint64), commitment=com, pok=pok,
+                    ped_g=vk.PedersenG if vk.has_commitment else None,
+                    ped_g_sigma_neg=vk.PedersenGSigmaNeg if vk.has_commitment else None)
+    if not ok:
+        raise ValueError("groth16.Verify: pairing check failed")

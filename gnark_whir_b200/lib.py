@@ -40,6 +40,9 @@ SIGNATURES = {
     "b200g16_bases_upload_g2": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
     "b200g16_bases_free": (None, [_vp]),
     "b200g16_bases_len": (_sz, [_vp]),
+    "b200g16_bases_precompute": (C.c_int, [_vp, _vp, C.c_int]),
+    "b200g16_bases_window": (C.c_int, [_vp]),
+    "b200g16_msm_plan": (C.c_int, [_vp, _vp, _sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200g16_bases_download": (C.c_int, [_vp, _sz, _sz, _vp]),
     "b200g16_fixed_base_mul_g1": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "b200g16_fixed_base_mul_g2": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -65,6 +68,9 @@ SIGNATURES = {
     "b200g16_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "b200g16_prove_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_prove_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200g16_pairing_check": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
+    "b200g16_pair": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "b200g16_verify": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -139,7 +145,14 @@ class PkDesc(C.Structure):
         ("g1_alpha", _vp), ("g1_beta", _vp), ("g1_delta", _vp), ("g2_beta", _vp), ("g2_delta", _vp),
         ("infinity_a", _vp), ("infinity_b", _vp), ("k_skip", _vp),
         ("partial", C.c_int), ("off_a", _sz), ("off_b", _sz), ("off_k", _sz), ("off_z", _sz),
+        ("precompute", C.c_int),
     ]
+
+
+class VkDesc(C.Structure):
+    """struct b200g16_vk_desc (include/b200g16.h)"""
+    _fields_ = [("g1_alpha", _vp), ("g2_beta", _vp), ("g2_gamma", _vp), ("g2_delta", _vp), ("g1_k", _vp), ("n_k", _sz),
+                ("ped_g", _vp), ("ped_g_sigma_neg", _vp)]
 
 
 class ProofOut(C.Structure):
@@ -167,6 +180,14 @@ class Bases:
 
     def __len__(self):
         return self.n
+
+    def precompute(self, window_bits=0):
+        """Attach a window table (b200g16_bases_precompute); returns the window width used."""
+        _check(load().b200g16_bases_precompute(self.ctx.h, self.handle, int(window_bits)))
+        return self.window()
+
+    def window(self):
+        return int(load().b200g16_bases_window(self.handle))
 
     def download(self, offset=0, n=None):
         n = self.n - offset if n is None else n
@@ -308,7 +329,7 @@ class Context:
 
     # -- Groth16 prove (pk resident; mirrors groth16_bn254.Prove after Solve)
     def pk_upload(self, log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2,
-                  infinity_a, infinity_b, k_skip, partial=False, offsets=(0, 0, 0, 0)):
+                  infinity_a, infinity_b, k_skip, partial=False, offsets=(0, 0, 0, 0), precompute=False):
         """A/B/K/Z/B2: numpy point arrays (host) or Bases (already resident, borrowed).
         partial=True: the vectors are entries [off, off+len) of the full key vectors
         (offsets = (off_a, off_b, off_k, off_z)); prove() then returns partial MSM sums."""
@@ -324,6 +345,7 @@ class Context:
         d = PkDesc()
         d.log2_domain, d.n_wires = log2_domain, n_wires
         d.partial = int(bool(partial))
+        d.precompute = int(bool(precompute))
         d.off_a, d.off_b, d.off_k, d.off_z = [int(x) for x in offsets]
         d.g1_a, d.res_a, d.n_a = vec(A, 8)
         d.g1_b, d.res_b, d.n_b = vec(B, 8)
@@ -373,6 +395,50 @@ class Context:
         _check(load().b200g16_prove_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)),
                                         _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
+
+    # -- pairing / verify (mirror bn254.PairingCheck, bn254.Pair, groth16.Verify)
+    def pairing_check(self, g1_points, g2_points):
+        p, q = _u64(g1_points, 8), _u64(g2_points, 16)
+        if p.shape[0] != q.shape[0]:
+            raise B200Error("pairing_check: len(P) != len(Q)")
+        ok = C.c_int()
+        _check(load().b200g16_pairing_check(self.h, _ptr(p), _ptr(q), p.shape[0], C.byref(ok)))
+        return bool(ok.value)
+
+    def pair(self, g1_points, g2_points):
+        """-> GT element, (6, 8) uint64: C0.B0, C0.B1, C0.B2, C1.B0, C1.B1, C1.B2 (gnark E12 order)"""
+        p, q = _u64(g1_points, 8), _u64(g2_points, 16)
+        if p.shape[0] != q.shape[0]:
+            raise B200Error("pair: len(P) != len(Q)")
+        out = np.zeros((6, 8), dtype=np.uint64)
+        _check(load().b200g16_pair(self.h, _ptr(p), _ptr(q), p.shape[0], _ptr(out)))
+        return out
+
+    def verify(self, alpha, beta2, gamma2, delta2, K, ar, bs, krs, public_inputs, commitment=None, pok=None,
+               ped_g=None, ped_g_sigma_neg=None):
+        keep = [_u64(alpha).reshape(8), _u64(beta2).reshape(16), _u64(gamma2).reshape(16), _u64(delta2).reshape(16),
+                _u64(K, 8)]
+        d = VkDesc()
+        d.g1_alpha, d.g2_beta, d.g2_gamma, d.g2_delta, d.g1_k = [_ptr(a) for a in keep]
+        d.n_k = keep[4].shape[0]
+        opt = [None if v is None else _u64(v).reshape(w) for v, w in ((ped_g, 16), (ped_g_sigma_neg, 16),
+                                                                        (commitment, 8), (pok, 8))]
+        d.ped_g = _ptr(opt[0]) if opt[0] is not None else None
+        d.ped_g_sigma_neg = _ptr(opt[1]) if opt[1] is not None else None
+        pts = [_u64(ar).reshape(8), _u64(bs).reshape(16), _u64(krs).reshape(8)]
+        pub = _u64(public_inputs, 4)
+        ok = C.c_int()
+        _check(load().b200g16_verify(self.h, C.byref(d), _ptr(pts[0]), _ptr(pts[1]), _ptr(pts[2]),
+                                     _ptr(opt[2]) if opt[2] is not None else None,
+                                     _ptr(opt[3]) if opt[3] is not None else None,
+                                     _ptr(pub) if pub.shape[0] else None, pub.shape[0], C.byref(ok)))
+        return bool(ok.value)
+
+    def msm_plan(self, bases, n=None):
+        """(window bits c, digits per scalar W) the library uses for an n-point MSM on `bases`."""
+        c, w = C.c_int(), C.c_int()
+        _check(load().b200g16_msm_plan(self.h, bases.handle, bases.n if n is None else n, C.byref(c), C.byref(w)))
+        return c.value, w.value
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
     def msm(self, bases, scalars, offset=0, n=None):

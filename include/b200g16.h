@@ -83,6 +83,9 @@ typedef struct b200g16_pk_desc {
    * the partial MSM sums (msm_*), to be added across GPUs and passed to b200g16_prove_finish. */
   int partial;
   size_t off_a, off_b, off_k, off_z;
+  /* != 0: b200g16_pk_upload attaches window tables (b200g16_bases_precompute, automatic width)
+   * to the point vectors it uploads itself; borrowed res_* vectors keep whatever they carry. */
+  int precompute;
 } b200g16_pk_desc;
 
 /* Proof{Ar, Bs, Krs} plus every intermediate MSM output, for parity checks against the
@@ -121,6 +124,23 @@ int b200g16_bases_upload_g1(b200g16_ctx* ctx, const uint64_t* points, size_t n, 
 int b200g16_bases_upload_g2(b200g16_ctx* ctx, const uint64_t* points, size_t n, b200g16_bases** out);
 void b200g16_bases_free(b200g16_bases* bases);
 size_t b200g16_bases_len(const b200g16_bases* bases);
+
+/* Attach a WINDOW TABLE to a resident vector: the vector grows from n points to W rows of n
+ * points, row k = 2^(c*k) * P_i (built on the GPU, c doublings + a shared inversion per
+ * point and row).  Every later MSM on it then needs no per-window bucket sets: digit k of
+ * scalar i addresses table entry (k, i), all digits accumulate into ONE set of 2^(c-1)
+ * buckets, and c can be wide (20-22 at n = 2^24: 12-13 adds per point instead of 15-16)
+ * because only one bucket set has to be reduced.  Costs W x the memory (n = 2^24, G1, c = 22:
+ * 12 GiB of the 180 GB) and one pass at upload time — the proving key is uploaded once and
+ * proved with many times.  window_bits = 0 picks c from n; otherwise 8 <= c <= 22.
+ * Results are bit-identical with and without a table (tests/test_gpu_msm.py). */
+int b200g16_bases_precompute(b200g16_ctx* ctx, b200g16_bases* bases, int window_bits);
+/* Window width of the attached table (0 = none). */
+int b200g16_bases_window(const b200g16_bases* bases);
+
+/* The Pippenger decomposition an n-point MSM on `bases` would use: c-bit signed digits,
+ * `windows` digits per scalar (= mixed additions per point).  Reporting only (bench.py). */
+int b200g16_msm_plan(const b200g16_ctx* ctx, const b200g16_bases* bases, size_t n, int* window_bits, int* windows);
 
 /* Copy points [offset, offset+n) of a resident vector back to the host (tests / sampling). */
 int b200g16_bases_download(const b200g16_bases* bases, size_t offset, size_t n, uint64_t* out_points);
@@ -250,6 +270,48 @@ int b200g16_prove_finish(const b200g16_pk* pk, const uint64_t msm_a[8], const ui
  * clobbered; h is left in d_a). */
 int b200g16_prove_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_a, void* d_b,
                       void* d_c, const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out);
+
+/* ---- pairing / Groth16 verify ----------------------------------------------------------- */
+/* groth16_bn254.VerifyingKey as Verify needs it (gnark backend/groth16/bn254/verify.go). */
+typedef struct b200g16_vk_desc {
+  const uint64_t* g1_alpha;         /* vk.G1.Alpha                    G1Affine              */
+  const uint64_t* g2_beta;          /* vk.G2.Beta, Gamma, Delta       G2Affine              */
+  const uint64_t* g2_gamma;
+  const uint64_t* g2_delta;
+  const uint64_t* g1_k;             /* vk.G1.K   n_k x G1Affine: K[0] is the constant-one wire,
+                                       then the public inputs, then (with a commitment) its wire */
+  size_t n_k;
+  const uint64_t* ped_g;            /* vk.CommitmentKeys[0].G          G2Affine, NULL if none */
+  const uint64_t* ped_g_sigma_neg;  /* vk.CommitmentKeys[0].GSigmaNeg  G2Affine, NULL if none */
+} b200g16_vk_desc;
+
+/* *ok_out = 1 iff prod_i e(g1_points[i], g2_points[i]) == 1.  Replaces gnark-crypto
+ * ecc/bn254 PairingCheck (optimal ate: Miller loop over 6u+2 + Frobenius lines, final
+ * exponentiation).  Points are checked (G1 on curve, G2 in the r-torsion subgroup); a failed
+ * check is an error (B200G16_ERR_ARG), like gnark-crypto's.  Host pointers; runs on the GPU,
+ * one thread per Miller loop — constant work per proof, not a throughput path. */
+int b200g16_pairing_check(b200g16_ctx* ctx, const uint64_t* g1_points, const uint64_t* g2_points, size_t n,
+                          int* ok_out);
+/* out_gt = prod_i e(g1_points[i], g2_points[i]) as gnark-crypto's GT = E12 in memory order
+ * C0.B0, C0.B1, C0.B2, C1.B0, C1.B1, C1.B2 (each E2 = A0, A1; Montgomery).  Replaces
+ * ecc/bn254 Pair, including the cofactor 2u(6u^2+3u+1) its FinalExponentiation carries. */
+int b200g16_pair(b200g16_ctx* ctx, const uint64_t* g1_points, const uint64_t* g2_points, size_t n,
+                 uint64_t out_gt[48]);
+/* groth16.Verify (reference mt.go:497; gnark backend/groth16/bn254/verify.go):
+ *   public_inputs : n_public fr.Elements (Montgomery) = the public witness WITHOUT the constant
+ *                   one wire, followed — when the circuit has a BSB22 commitment — by the
+ *                   commitment challenge hash_to_field(commitment || committed publics), which
+ *                   the caller computes (gnark_whir_b200/groth16.py commitment_challenge);
+ *                   n_public + 1 must equal vk.n_k (else an error, gnark's "invalid witness size")
+ *   commitment, commitment_pok : proof.Commitments[0], proof.CommitmentPok (NULL, NULL if none)
+ * Checks: proof points valid (Ar, Krs on G1; Bs in the G2 subgroup), the Pedersen proof of
+ * knowledge e(commitment, GSigmaNeg) e(pok, G) == 1, and
+ * e(Ar, Bs) e(-kSum, gamma) e(-Krs, delta) e(-alpha, beta) == 1 with kSum = K[0] +
+ * MultiExp(K[1:], public_inputs) + commitment (the MSM runs through b200g16's Pippenger).
+ * *ok_out = 1 for a valid proof, 0 for an invalid one (gnark returns an error value there). */
+int b200g16_verify(b200g16_ctx* ctx, const b200g16_vk_desc* vk, const uint64_t ar[8], const uint64_t bs[16],
+                   const uint64_t krs[8], const uint64_t* commitment, const uint64_t* commitment_pok,
+                   const uint64_t* public_inputs, size_t n_public, int* ok_out);
 
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */

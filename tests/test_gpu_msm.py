@@ -130,3 +130,61 @@ def test_msm_g2_small_vs_naive(ctx, rng, n):
 def test_msm_g2_known_dlog(ctx, rng, mix):
     out, exp = _known_dlog_case(ctx, rng, 1 << 12, 2, mix)
     assert np.array_equal(out, exp)
+
+
+# ---- window tables (b200g16_bases_precompute): same results, bit for bit, as without a table
+@pytest.mark.parametrize("c", [0, 8, 11, 16, 22])
+def test_msm_g1_window_table_matches_plain(ctx, rng, c):
+    n = 300
+    ks, pts = _rand_points(rng, n)
+    pts[7] = None                      # an infinity base stays infinity in every row
+    pts[9] = pts[8]                    # repeated base
+    ss = [rng.randrange(R) for _ in range(n)]
+    ss[0], ss[1], ss[2], ss[3] = 0, 1, R - 1, 1
+    bases = ctx.upload_g1(bn.g1_to_array(pts))
+    plain = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    used = bases.precompute(c)
+    assert used == (c if c else bases.window()) and 8 <= used <= 22
+    assert np.array_equal(bases.download(), bn.g1_to_array(pts)), "row 0 must stay the original bases"
+    out = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    assert np.array_equal(out, plain)
+    assert np.array_equal(out, bn.g1_to_array([bn.g1_msm_naive(pts, ss)])[0])
+    # sub-range of a table-carrying vector
+    out = ctx.msm(bases, bn.fr_to_mont_array(ss[5:40]), offset=5)
+    assert np.array_equal(out, bn.g1_to_array([bn.g1_msm_naive(pts[5:40], ss[5:40])])[0])
+    # a second precompute is refused
+    with pytest.raises(Exception):
+        bases.precompute(c)
+    bases.free()
+
+
+@pytest.mark.parametrize("mix", ["uniform", "whir", "ones"])
+def test_msm_g1_window_table_known_dlog(ctx, rng, mix):
+    n = 1 << 15
+    ks = [rng.randrange(1, R) for _ in range(n)]
+    if mix == "uniform":
+        ss = [rng.randrange(R) for _ in range(n)]
+    elif mix == "ones":
+        ss = [1] * n
+    else:
+        ss = [rng.randrange(2) if (u := rng.random()) < 0.4 else rng.randrange(256) if u < 0.7 else rng.randrange(R)
+              for _ in range(n)]
+    bases = ctx.fixed_base_mul(bn.g1_to_array([bn.G1_GEN])[0], bn.fr_to_mont_array(ks), group=1, resident=True)
+    bases.precompute(0)
+    out = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    bases.free()
+    assert np.array_equal(out, bn.g1_to_array([bn.g1_mul(bn.G1_GEN, sum(k * s for k, s in zip(ks, ss)) % R)])[0])
+
+
+@pytest.mark.parametrize("c", [0, 9])
+def test_msm_g2_window_table(ctx, rng, c):
+    n = 1 << 10
+    ks = [rng.randrange(1, R) for _ in range(n)]
+    ss = [rng.randrange(R) for _ in range(n)]
+    bases = ctx.fixed_base_mul(bn.g2_to_array([bn.G2_GEN])[0], bn.fr_to_mont_array(ks), group=2, resident=True)
+    plain = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    bases.precompute(c)
+    out = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    bases.free()
+    assert np.array_equal(out, plain)
+    assert np.array_equal(out, bn.g2_to_array([bn.g2_mul(bn.G2_GEN, sum(k * s for k, s in zip(ks, ss)) % R)])[0])

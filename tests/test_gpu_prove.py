@@ -110,6 +110,23 @@ def test_prove_rejects_mismatched_inputs(ctx):
         pk.free()
 
 
+def test_prove_with_window_tables_is_identical(ctx):
+    """pk uploaded with precompute=1 (window tables on A, B1, K, Z, B2): every MSM output and the
+    proof must equal the table-free prove bit for bit."""
+    r1cs, w, tw, r, s = _case(91, 300, 4, False)
+    pk, _ = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        a, b, c = g16.solve_abc(r1cs, w)
+        args = (g16.fr_array(w), g16.fr_array(a), g16.fr_array(b), g16.fr_array(c), g16.fr_array([r])[0], g16.fr_array([s])[0])
+        plain, _ = ctx.prove(pk.device_handle(ctx), *args)
+        pk.free()
+        tabled, _ = ctx.prove(pk.device_handle(ctx, precompute=True), *args)
+        for k in plain:
+            assert np.array_equal(plain[k], tabled[k]), k
+    finally:
+        pk.free()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_prove_equals_single_gpu_prove(ctx, world):
     """Point-range shards of the proving key (config 5): the shards' partial MSM sums, added and

@@ -141,5 +141,6 @@ def test_host_mirror_layout_and_hash_agree_with_oracle(rng):
     assert g16.commitment_challenge(np.zeros(8, np.uint64), pub) == og.commitment_challenge(None, pub)
     r1cs, w = og.synthetic_r1cs(9, 2, rng)
     assert g16.solve_abc(r1cs, w) == og.solve_abc(r1cs, w)
-    with pytest.raises(NotImplementedError):
-        g16.Verify(None, None, None)
+    # Verify needs a device context: no CPU fallback behind the host mirror
+    with pytest.raises(AttributeError):
+        g16.Verify(None, g16.Proof(None, None, None), g16.VerifyingKey(None, None, None, None, None), [])
