@@ -190,7 +190,12 @@ int b200g16_init(int device, b200g16_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   B200_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  B200_CUDA(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev) B200_CUDA(cudaEventCreate(&ev));
+  for (int i = 0; i < 2; i++) {
+    B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_front[i], cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming));
+  }
   *out = ctx;
   return 0;
 }
@@ -199,13 +204,17 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->msm.counts, &ctx->msm.partials,
-                    &ctx->msm.buckets, &ctx->msm.chunks,  &ctx->msm.windows, &ctx->msm.misc,   &ctx->msm.tasks,
+  cudaStreamSynchronize(ctx->tail_stream);
+  DevBuf* bufs[] = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->msm.counts[0], &ctx->msm.counts[1],
+                    &ctx->msm.partials[0], &ctx->msm.partials[1], &ctx->msm.chunks[0], &ctx->msm.chunks[1],
+                    &ctx->msm.misc[0], &ctx->msm.misc[1], &ctx->msm.tasks[0], &ctx->msm.tasks[1],
                     &ctx->ntt.a,       &ctx->ntt.b,       &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->io_a,
                     &ctx->io_b,        &ctx->io_c};
   for (DevBuf* b : bufs) b->release();
   if (ctx->msm.pinned) cudaFreeHost(ctx->msm.pinned);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
+  cudaStreamDestroy(ctx->tail_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -65,7 +65,9 @@ struct DevBuf {
 };
 
 struct MsmWorkspace {
-  DevBuf scalars, digits, entries, counts, partials, buckets, chunks, windows, misc, tasks;
+  // everything the "tail" of an MSM reads (merge of split buckets + bucket reduction) exists twice: the
+  // tail runs on a second stream while the next MSM's sort + accumulate ("front") fills the other set
+  DevBuf scalars, digits, entries, counts[2], partials[2], chunks[2], misc[2], tasks[2];
   void* pinned = nullptr;  // small host staging for window sums
   size_t pinned_cap = 0;
 };
@@ -95,6 +97,10 @@ struct b200g16_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t tail_stream = nullptr;   // bucket reductions (latency-bound, few threads) overlap the next MSM
+  cudaEvent_t ev_front[2] = {}, ev_tail[2] = {};
+  bool tail_pending[2] = {false, false};
+  int msm_parity = 0;
   cudaEvent_t ev[18] = {};
   std::mutex mu;  // one call at a time per ctx (gnark calls MSMs from several goroutines)
   b200::MsmWorkspace msm;

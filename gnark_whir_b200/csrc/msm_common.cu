@@ -42,10 +42,12 @@ int msm_pick_window(size_t n) {
 int msm_pick_table_window(size_t n) {
   int best = 8;
   double best_cost = 1e300;
-  for (int c = 8; c <= 22; c++) {
+  // measured on B200 (gpurun_out probe7: 2^16..2^24): c = 20 at n >= 2^22, 19 at 2^20, 17 at 2^18; beyond
+  // c = 21 the single bucket set's scatter targets (4 W n bytes) stop fitting the L2 window by window
+  for (int c = 8; c <= 21; c++) {
     const int W = msm_num_windows(c);
     if ((double)n * W >= 2.0e9) continue;
-    double cost = (double)W * (double)n + 24.0 * (double)(1u << (c - 1));
+    double cost = (double)W * (double)n + 4.0 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
@@ -114,14 +116,14 @@ __global__ void __launch_bounds__(256) k_digits(const Fr* __restrict__ scalars, 
   }
 }
 
-// task size.  Many buckets (nb >= target): evenly loaded buckets stay one task each (seg = 2 x mean),
+// task size.  Many buckets (nb >= target / 2): evenly loaded buckets stay one task each (seg = 2 x mean),
 // and a skewed input (few huge buckets) still yields >= target tasks.  Few buckets (window tables with
 // a narrow window, small windows): the buckets are cut so that ~target tasks exist at all — otherwise
 // the accumulate kernel would run with a fraction of the SMs' threads.  totals[4] = seg.
 __global__ void k_pick_seg(uint32_t* __restrict__ totals, uint32_t nb, uint32_t target) {
   uint32_t total = totals[3];
   uint32_t a = 2u * (total / nb) + 2u, b = total / target + 1u;
-  uint32_t seg = (nb >= target && a > b) ? a : b;
+  uint32_t seg = (nb >= target / 2 && a > b) ? a : b;
   totals[4] = seg < 32u ? 32u : seg;
 }
 

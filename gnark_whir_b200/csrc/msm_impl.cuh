@@ -97,12 +97,13 @@ __global__ void __launch_bounds__(128, (sizeof(F) > 32) ? 2 : 4) k_accumulate(co
   partials[t] = acc;
 }
 
-// Merge the partials of buckets that were split into several tasks: a fan-in-16 tree over the
-// (contiguous) partials of each bucket, one launch per level (stride = 16^level).  Thread t owns task
-// t; at a level only local indices that are multiples of 16*stride do work, reading slots no other
+// Merge the partials of buckets that were split into several tasks: a fan-in-4 tree over the
+// (contiguous) partials of each bucket, one launch per level (stride = 4^level: 3 dependent additions
+// per level, a quarter of the lanes busy).  Thread t owns task
+// t; at a level only local indices that are multiples of 4*stride do work, reading slots no other
 // thread writes in the same launch.  After the last level the bucket's sum sits in its first partial.
 // totals[5] = largest #tasks of any bucket (written by k_tasks), so idle levels exit immediately.
-constexpr uint32_t MERGE_FANIN = 16;
+constexpr uint32_t MERGE_FANIN = 4;
 
 template <class F>
 __global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partials,
@@ -150,9 +151,9 @@ __global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ part
   chunks[g] = acc;
 }
 
-// plain sums, fan-in 16: out[w][g] = sum_{j<16} in[w][16 g + j]   (len_in items per window, thread per g);
-// applied until one item per window is left
-constexpr uint32_t SUM_FANIN = 16;
+// plain sums, fan-in 4: out[w][g] = sum_{j<4} in[w][4 g + j]   (len_in items per window, thread per g);
+// applied until one item per window is left (3 dependent additions per level)
+constexpr uint32_t SUM_FANIN = 4;
 
 template <class F>
 __global__ void __launch_bounds__(128) k_sum_pass(const XYZZ<F>* __restrict__ in, uint32_t len_in, uint32_t len_out,
@@ -199,21 +200,26 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   if ((double)n * cfg.W >= 4.0e9) return fail(B200G16_ERR_ARG, "msm: n*W overflows 32-bit entry index");
   size_t m_max = n * (size_t)cfg.W;
   cfg.target_tasks = (uint32_t)ctx->sm_count * 2048u;  // ~4 waves of 512 resident threads per SM
-  cfg.ch = cfg.nbw < 32 ? cfg.nbw : (cfg.nbw >= (1u << 17) ? 64 : 32);
+  // buckets per reduce thread: the reduction is a serial chain of 2 ch + ~1.5 c group operations per
+  // thread, so small bucket sets (latency-bound) get short chunks, large ones amortise the lo * running
+  // multiplication over more buckets
+  cfg.ch = cfg.nbw < 8 ? cfg.nbw : (cfg.nb <= (1u << 19) ? 8 : 32);
   cfg.nch = cfg.nbw / cfg.ch;
   // #tasks = sum ceil(cnt/seg) <= nb + total/seg <= nb + target (k_pick_seg keeps seg >= total/target)
   size_t max_tasks = (size_t)cfg.nb + cfg.target_tasks + 64;
 
   MsmWorkspace& ws = ctx->msm;
+  const int par = ctx->msm_parity;
+  ctx->msm_parity ^= 1;
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
   B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
-  B200_TRY(ws.counts.ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
+  B200_TRY(ws.counts[par].ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
   // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
   const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
-  B200_TRY(ws.misc.ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
-  B200_TRY(ws.tasks.ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
-  B200_TRY(ws.partials.ensure(max_tasks * sizeof(XYZZ<F>)));
-  B200_TRY(ws.chunks.ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
+  B200_TRY(ws.misc[par].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
+  B200_TRY(ws.tasks[par].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
+  B200_TRY(ws.partials[par].ensure(max_tasks * sizeof(XYZZ<F>)));
+  B200_TRY(ws.chunks[par].ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
   if (ws.pinned_cap < MSM_SLOTS * slot_bytes) {
     if (ws.pinned) cudaFreeHost(ws.pinned);
@@ -222,55 +228,74 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   }
   if (cfg.W > MSM_MAX_WINDOWS - 2) return fail(B200G16_ERR_ARG, "msm: too many windows");
 
-  uint32_t* counts = ws.counts.as<uint32_t>();
+  uint32_t* counts = ws.counts[par].as<uint32_t>();
   uint32_t* offsets = counts + cfg.nb;
   uint32_t* cursor = offsets + cfg.nb;
   uint32_t* task_off = cursor + cfg.nb;
-  uint32_t* totals = ws.misc.as<uint32_t>();
+  uint32_t* totals = ws.misc[par].as<uint32_t>();
   int32_t* digits = ws.digits.as<int32_t>();
   uint32_t* entries = ws.entries.as<uint32_t>();
-  uint32_t* task_bucket = ws.tasks.as<uint32_t>();
+  uint32_t* task_bucket = ws.tasks[par].as<uint32_t>();
   uint32_t* task_order = task_bucket + max_tasks;
-  XYZZ<F>* partials = ws.partials.as<XYZZ<F>>();
-  XYZZ<F>* chunks = ws.chunks.as<XYZZ<F>>();
+  XYZZ<F>* partials = ws.partials[par].as<XYZZ<F>>();
+  XYZZ<F>* chunks = ws.chunks[par].as<XYZZ<F>>();
   XYZZ<F>* windows = nullptr;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->stream, tail = ctx->tail_stream;
   uint32_t n32 = (uint32_t)n;
   int ev = 0;
   auto mark = [&]() { if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
+  // buffer set `par` may still be read by the tail of the MSM before last
+  if (ctx->tail_pending[par]) B200_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[par], 0));
 
   B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
                           task_bucket, task_order, (uint32_t)max_tasks,
-                          reinterpret_cast<uint32_t*>(ws.misc.as<char>() + scan_off),
+                          reinterpret_cast<uint32_t*>(ws.misc[par].as<char>() + scan_off),
                           record_events ? &ev : nullptr));
   k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_order, task_bucket, offsets, counts, task_off,
                                                          totals, partials);
   mark();
+  // ---- tail: merge of split buckets + bucket reduction on the second stream (few active threads, long
+  // dependency chains), so that the next MSM's sort + accumulate on `st` overlap it
+  B200_CUDA(cudaEventRecord(ctx->ev_front[par], st));
+  B200_CUDA(cudaStreamWaitEvent(tail, ctx->ev_front[par], 0));
   int merge_levels = 0;
   for (uint64_t stride = 1; stride < max_tasks; stride *= MERGE_FANIN, merge_levels++)
-    k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(partials, task_bucket, counts, task_off, totals,
-                                                           (uint32_t)stride);
-  mark();
-  k_reduce<F><<<cdiv((size_t)cfg.Wr * cfg.nch, 128), 128, 0, st>>>(partials, counts, task_off, cfg.Wr, cfg.nbw, cfg.ch,
-                                                                    cfg.nch, cfg.c, chunks);
+    k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, tail>>>(partials, task_bucket, counts, task_off, totals,
+                                                             (uint32_t)stride);
+  if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
+  k_reduce<F><<<cdiv((size_t)cfg.Wr * cfg.nch, 128), 128, 0, tail>>>(partials, counts, task_off, cfg.Wr, cfg.nbw, cfg.ch,
+                                                                      cfg.nch, cfg.c, chunks);
   // chunk sums -> one sum per window: ping-pong between the two halves of the chunk buffer
   XYZZ<F>* cur = chunks;
   XYZZ<F>* nxt = chunks + (size_t)cfg.Wr * cfg.nch;
   int sum_levels = 0;
   for (uint32_t len = cfg.nch; len > 1; sum_levels++) {
     const uint32_t len_out = (len + SUM_FANIN - 1) / SUM_FANIN, total_out = (uint32_t)cfg.Wr * len_out;
-    k_sum_pass<F><<<cdiv(total_out, 128), 128, 0, st>>>(cur, len, len_out, total_out, nxt);
+    k_sum_pass<F><<<cdiv(total_out, 128), 128, 0, tail>>>(cur, len, len_out, total_out, nxt);
     XYZZ<F>* t = cur; cur = nxt; nxt = t;
     len = len_out;
   }
   windows = cur;  // Wr items
-  mark();
+  if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
   ctx->launches += 2 + merge_levels + sum_levels;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.Wr * sizeof(XYZZ<F>),
-                            cudaMemcpyDeviceToHost, st));
+                            cudaMemcpyDeviceToHost, tail));
+  B200_CUDA(cudaEventRecord(ctx->ev_tail[par], tail));
+  ctx->tail_pending[par] = true;
   if (record_events) ctx->timings.n = -(ev - 1);  // negative: events recorded, not yet resolved
   *cfg_out = cfg;
+  return 0;
+}
+
+// Make ctx->stream wait for every outstanding bucket reduction: after this, synchronising ctx->stream
+// guarantees all enqueued MSM results are in their pinned slots.
+inline int msm_join(b200g16_ctx* ctx) {
+  for (int p = 0; p < 2; p++)
+    if (ctx->tail_pending[p]) {
+      B200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail[p], 0));
+      ctx->tail_pending[p] = false;
+    }
   return 0;
 }
 
@@ -303,6 +328,7 @@ int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, 
   MsmCfg cfg;
   ctx->timings.n = 0;
   B200_TRY(msm_enqueue<F>(ctx, d_bases, tab, d_scalars, n, 0, &cfg, true));
+  B200_TRY(msm_join(ctx));
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
   msm_resolve_timings(ctx);
   return msm_collect<F>(ctx, 0, cfg, out);

@@ -210,6 +210,7 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
     }
     mark();
   }
+  B200_TRY(msm_join(ctx));
   B200_CUDA(cudaStreamSynchronize(st));
   *ev_io = ev;
 
