@@ -33,7 +33,38 @@ __constant__ uint64_t kRC[24] = {
 
 __device__ __forceinline__ uint64_t rol64(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
 
-__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
+// 2^k, read through the constant bank so ptxas cannot turn the multiplications below back into shifts
+__constant__ uint32_t kPow2[32] = {1u << 0,  1u << 1,  1u << 2,  1u << 3,  1u << 4,  1u << 5,  1u << 6,  1u << 7,
+                                   1u << 8,  1u << 9,  1u << 10, 1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15,
+                                   1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21, 1u << 22, 1u << 23,
+                                   1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31};
+
+// 64-bit rotation on the FMA pipe: (x << k) = x * 2^k (IMAD), (x >> (32 - k)) = umulhi(x, 2^k) (IMAD.HI);
+// the two parts of each half never overlap, so the OR is the multiply-add's addition.  Keccak-f is bound
+// by the ALU pipe (LOP3 + SHF: 81% busy, FMA pipe 5% — profiles/r01b_ncu_full_summary.txt); moving part of
+// the rotations over balances the two pipes.
+template <int N>
+__device__ __forceinline__ uint64_t rol64_fma(uint64_t v) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  if (N >= 32) { uint32_t t = lo; lo = hi; hi = t; }
+  constexpr int K = N & 31;
+  if (K == 0) return ((uint64_t)hi << 32) | lo;
+  const uint32_t m = kPow2[K];
+  uint32_t nlo = lo * m + __umulhi(hi, m);
+  uint32_t nhi = hi * m + __umulhi(lo, m);
+  return ((uint64_t)nhi << 32) | nlo;
+}
+
+// rotation `IDX` (0..4: theta's rotations by 1, 5..28: the rho rotation of lane IDX-4) goes to the FMA
+// pipe when bit IDX of MASK is set
+template <uint32_t MASK, int IDX, int N>
+__device__ __forceinline__ uint64_t rolx(uint64_t v) {
+  if constexpr ((MASK >> IDX) & 1u) return rol64_fma<N>(v);
+  else return rol64(v, N);
+}
+
+template <uint32_t MASK>
+__device__ __forceinline__ void keccak_f1600_t(uint64_t (&a)[25]) {
 #pragma unroll
   for (int rnd = 0; rnd < 24; rnd++) {
     uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20];
@@ -41,37 +72,37 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
     uint64_t c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22];
     uint64_t c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23];
     uint64_t c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
-    uint64_t d0 = c4 ^ rol64(c1, 1);
-    uint64_t d1 = c0 ^ rol64(c2, 1);
-    uint64_t d2 = c1 ^ rol64(c3, 1);
-    uint64_t d3 = c2 ^ rol64(c4, 1);
-    uint64_t d4 = c3 ^ rol64(c0, 1);
+    uint64_t d0 = c4 ^ rolx<MASK, 0, 1>(c1);
+    uint64_t d1 = c0 ^ rolx<MASK, 1, 1>(c2);
+    uint64_t d2 = c1 ^ rolx<MASK, 2, 1>(c3);
+    uint64_t d3 = c2 ^ rolx<MASK, 3, 1>(c4);
+    uint64_t d4 = c3 ^ rolx<MASK, 4, 1>(c0);
     // theta + rho + pi:  b[y + 5((2x+3y)%5)] = rol(a[x+5y] ^ d[x], ROT[x][y])
     uint64_t b0 = a[0] ^ d0;
-    uint64_t b10 = rol64(a[1] ^ d1, 1);
-    uint64_t b20 = rol64(a[2] ^ d2, 62);
-    uint64_t b5 = rol64(a[3] ^ d3, 28);
-    uint64_t b15 = rol64(a[4] ^ d4, 27);
-    uint64_t b16 = rol64(a[5] ^ d0, 36);
-    uint64_t b1 = rol64(a[6] ^ d1, 44);
-    uint64_t b11 = rol64(a[7] ^ d2, 6);
-    uint64_t b21 = rol64(a[8] ^ d3, 55);
-    uint64_t b6 = rol64(a[9] ^ d4, 20);
-    uint64_t b7 = rol64(a[10] ^ d0, 3);
-    uint64_t b17 = rol64(a[11] ^ d1, 10);
-    uint64_t b2 = rol64(a[12] ^ d2, 43);
-    uint64_t b12 = rol64(a[13] ^ d3, 25);
-    uint64_t b22 = rol64(a[14] ^ d4, 39);
-    uint64_t b23 = rol64(a[15] ^ d0, 41);
-    uint64_t b8 = rol64(a[16] ^ d1, 45);
-    uint64_t b18 = rol64(a[17] ^ d2, 15);
-    uint64_t b3 = rol64(a[18] ^ d3, 21);
-    uint64_t b13 = rol64(a[19] ^ d4, 8);
-    uint64_t b14 = rol64(a[20] ^ d0, 18);
-    uint64_t b24 = rol64(a[21] ^ d1, 2);
-    uint64_t b9 = rol64(a[22] ^ d2, 61);
-    uint64_t b19 = rol64(a[23] ^ d3, 56);
-    uint64_t b4 = rol64(a[24] ^ d4, 14);
+    uint64_t b10 = rolx<MASK, 5, 1>(a[1] ^ d1);
+    uint64_t b20 = rolx<MASK, 6, 62>(a[2] ^ d2);
+    uint64_t b5 = rolx<MASK, 7, 28>(a[3] ^ d3);
+    uint64_t b15 = rolx<MASK, 8, 27>(a[4] ^ d4);
+    uint64_t b16 = rolx<MASK, 9, 36>(a[5] ^ d0);
+    uint64_t b1 = rolx<MASK, 10, 44>(a[6] ^ d1);
+    uint64_t b11 = rolx<MASK, 11, 6>(a[7] ^ d2);
+    uint64_t b21 = rolx<MASK, 12, 55>(a[8] ^ d3);
+    uint64_t b6 = rolx<MASK, 13, 20>(a[9] ^ d4);
+    uint64_t b7 = rolx<MASK, 14, 3>(a[10] ^ d0);
+    uint64_t b17 = rolx<MASK, 15, 10>(a[11] ^ d1);
+    uint64_t b2 = rolx<MASK, 16, 43>(a[12] ^ d2);
+    uint64_t b12 = rolx<MASK, 17, 25>(a[13] ^ d3);
+    uint64_t b22 = rolx<MASK, 18, 39>(a[14] ^ d4);
+    uint64_t b23 = rolx<MASK, 19, 41>(a[15] ^ d0);
+    uint64_t b8 = rolx<MASK, 20, 45>(a[16] ^ d1);
+    uint64_t b18 = rolx<MASK, 21, 15>(a[17] ^ d2);
+    uint64_t b3 = rolx<MASK, 22, 21>(a[18] ^ d3);
+    uint64_t b13 = rolx<MASK, 23, 8>(a[19] ^ d4);
+    uint64_t b14 = rolx<MASK, 24, 18>(a[20] ^ d0);
+    uint64_t b24 = rolx<MASK, 25, 2>(a[21] ^ d1);
+    uint64_t b9 = rolx<MASK, 26, 61>(a[22] ^ d2);
+    uint64_t b19 = rolx<MASK, 27, 56>(a[23] ^ d3);
+    uint64_t b4 = rolx<MASK, 28, 14>(a[24] ^ d4);
     // chi
     a[0] = b0 ^ (~b1 & b2);   a[1] = b1 ^ (~b2 & b3);   a[2] = b2 ^ (~b3 & b4);
     a[3] = b3 ^ (~b4 & b0);   a[4] = b4 ^ (~b0 & b1);
@@ -88,9 +119,19 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
   }
 }
 
+// Which rotations run on the FMA pipe.  Measured on B200, 2^22 states (tools/gpu_probe9.py): none 2.81,
+// all 29 2.86 (FMA-bound), theta's five 2.83, one rho rotation in three 2.91, every other 2.92, two in
+// three 2.95 Gperm/s.  The gain is small because IMAD.HI issues at half rate and the two pipes overlap
+// only partly (b200g16_pipe_probe mode 5), but it is free.
+#ifndef B200_KECCAK_FMA_MASK
+#define B200_KECCAK_FMA_MASK 0x1b6db6d0u
+#endif
+__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) { keccak_f1600_t<B200_KECCAK_FMA_MASK>(a); }
+
 // ---- raw batch: states[i][25] permuted in place.  A warp stages its 32 states (6400
 // contiguous bytes) through shared memory so the global accesses are fully coalesced.
 constexpr int KF_THREADS = 128;
+template <uint32_t MASK>
 __global__ void __launch_bounds__(KF_THREADS) k_keccak_f_batch(uint64_t* __restrict__ states, size_t n) {
   __shared__ uint64_t sm[KF_THREADS / 32][32 * 25];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +150,7 @@ __global__ void __launch_bounds__(KF_THREADS) k_keccak_f_batch(uint64_t* __restr
   if (lane < in_warp) {
 #pragma unroll
     for (int l = 0; l < 25; l++) a[l] = sm[warp][lane * 25 + l];
-    keccak_f1600(a);
+    keccak_f1600_t<MASK>(a);
 #pragma unroll
     for (int l = 0; l < 25; l++) sm[warp][lane * 25 + l] = a[l];
   }
@@ -225,7 +266,7 @@ __global__ void __launch_bounds__(128) k_merkle_paths(const uint8_t* __restrict_
 int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n) {
   if (n == 0) return 0;
   unsigned grid = (unsigned)((n + KF_THREADS - 1) / KF_THREADS);
-  k_keccak_f_batch<<<grid, KF_THREADS, 0, ctx->stream>>>(d_states, n);
+  k_keccak_f_batch<B200_KECCAK_FMA_MASK><<<grid, KF_THREADS, 0, ctx->stream>>>(d_states, n);
   ctx->launches++;
   B200_CUDA(cudaGetLastError());
   return 0;
