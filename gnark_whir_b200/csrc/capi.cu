@@ -1,17 +1,17 @@
 // extern "C" surface of libb200g16 (see include/b200g16.h for the contract and the
 // gnark / gnark-crypto routines each entry point replaces).
-#include "common.cuh"
-#include "ec.cuh"
+#include "msm_impl.cuh"
 
 namespace b200 {
-template <class F>
-int msm_device(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, const Fr* d_scalars, size_t n,
-               Affine<F>* out);
-template <class F>
-int msm_build_table(b200g16_ctx* ctx, Affine<F>* table, size_t n, int c, int W);
-int msm_pick_table_window(size_t n);
-int msm_num_windows(int c);
-int msm_pick_window(size_t n);
+// instantiated in msm_g1.cu / msm_g2.cu
+extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
+extern template int msm_device<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, Affine<Fp>*);
+extern template int msm_build_table<Fp>(b200g16_ctx*, Affine<Fp>*, size_t, int, int);
+extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
+extern template int msm_device<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, Affine<Fp2>*);
+extern template int msm_build_table<Fp2>(b200g16_ctx*, Affine<Fp2>*, size_t, int, int);
 
 template <class F>
 int fixed_base_mul_device(b200g16_ctx* ctx, const Affine<F>& base, const Fr* d_scalars, size_t n, Affine<F>* d_out);
@@ -60,6 +60,12 @@ static int fixed_base_entry(b200g16_ctx* ctx, const uint64_t* base, const uint64
   return st;
 }
 
+// Host scalars of a large MSM are uploaded in MSM_PIPE_CHUNKS pieces on a copy stream; piece j's
+// sub-MSM (its own point sub-range, its own result slot) runs while piece j+1 is still crossing PCIe,
+// and the host adds the partial results.  Below MSM_PIPE_MIN points one copy + one MSM is faster.
+constexpr size_t MSM_PIPE_MIN = (size_t)1 << 22;
+constexpr int MSM_PIPE_CHUNKS = 4;
+
 template <class F>
 static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, size_t offset, const void* scalars,
                      bool scalars_on_device, size_t n, uint64_t* out) {
@@ -70,23 +76,44 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     return fail(B200G16_ERR_ARG, "msm: range [%zu,%zu) exceeds %zu bases", offset, offset + n, bases->n);
   std::lock_guard<std::mutex> lock(ctx->mu);
   B200_CUDA(cudaSetDevice(ctx->device));
-  const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
-  if (!scalars_on_device && n) {
-    B200_TRY(ctx->msm.scalars.ensure(n * sizeof(Fr)));
-    B200_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    d_scalars = ctx->msm.scalars.as<Fr>();
-  }
-  Affine<F> res;
   MsmTable tab;
   const MsmTable* tp = nullptr;
-  const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
-  if (bases->tab_c) {
-    tab.c = bases->tab_c; tab.W = bases->tab_W; tab.stride = (uint32_t)bases->n; tab.off = (uint32_t)offset;
-    tp = &tab;
+  Affine<F> res;
+  if (!scalars_on_device && n >= MSM_PIPE_MIN) {
+    B200_TRY(ctx->msm.scalars.ensure(n * sizeof(Fr)));
+    const Fr* h = reinterpret_cast<const Fr*>(scalars);
+    Fr* d = ctx->msm.scalars.as<Fr>();
+    MsmCfg cfg[MSM_PIPE_CHUNKS];
+    size_t lo[MSM_PIPE_CHUNKS + 1];
+    for (int j = 0; j <= MSM_PIPE_CHUNKS; j++) lo[j] = n * (size_t)j / MSM_PIPE_CHUNKS;
+    ctx->timings.n = 0;
+    for (int j = 0; j < MSM_PIPE_CHUNKS; j++) {
+      const size_t m = lo[j + 1] - lo[j];
+      B200_CUDA(cudaMemcpyAsync(d + lo[j], h + lo[j], m * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      B200_CUDA(cudaEventRecord(ctx->ev_copy[j], ctx->copy_stream));
+      B200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[j], 0));
+      const Affine<F>* pts = msm_operand<F>(bases, offset + lo[j], &tab, &tp);
+      B200_TRY(msm_enqueue<F>(ctx, pts, tp, d + lo[j], m, j, &cfg[j], false));
+    }
+    B200_TRY(msm_join(ctx));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int j = 0; j < MSM_PIPE_CHUNKS; j++) {
+      Affine<F> part;
+      B200_TRY(msm_collect<F>(ctx, j, cfg[j], &part));
+      acc.madd(part);
+    }
+    res = acc.to_affine();
   } else {
-    pts += offset;
+    const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
+    if (!scalars_on_device && n) {
+      B200_TRY(ctx->msm.scalars.ensure(n * sizeof(Fr)));
+      B200_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+      d_scalars = ctx->msm.scalars.as<Fr>();
+    }
+    const Affine<F>* pts = msm_operand<F>(bases, offset, &tab, &tp);
+    B200_TRY(msm_device<F>(ctx, pts, tp, d_scalars, n, &res));
   }
-  B200_TRY(msm_device<F>(ctx, pts, tp, d_scalars, n, &res));
   memcpy(out, &res, sizeof(res));
   return 0;
 }
@@ -190,7 +217,13 @@ int b200g16_init(int device, b200g16_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   B200_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  B200_CUDA(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
+  {  // the tails are short, latency-bound kernels: let them run ahead of the next MSM's bulk work
+    int prio_lo = 0, prio_hi = 0;
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    B200_CUDA(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, prio_hi));
+  }
+  B200_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : ctx->ev_copy) B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : ctx->ev) B200_CUDA(cudaEventCreate(&ev));
   for (int i = 0; i < 2; i++) {
     B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_front[i], cudaEventDisableTiming));
@@ -214,6 +247,8 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   if (ctx->msm.pinned) cudaFreeHost(ctx->msm.pinned);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
+  for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->tail_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -98,6 +98,8 @@ struct b200g16_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t tail_stream = nullptr;   // bucket reductions (latency-bound, few threads) overlap the next MSM
+  cudaStream_t copy_stream = nullptr;   // H2D of host scalars, pipelined against the MSM of the previous piece
+  cudaEvent_t ev_copy[4] = {};
   cudaEvent_t ev_front[2] = {}, ev_tail[2] = {};
   bool tail_pending[2] = {false, false};
   int msm_parity = 0;

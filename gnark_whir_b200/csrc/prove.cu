@@ -8,8 +8,10 @@
 //
 // Device timeline (one stream): H2D(wires,a,b,c) -> gather wire values into the A / B / K
 // scalar vectors (gnark's filter by pk.InfinityA / pk.InfinityB and by public+committed wires)
-// -> computeH -> MSM A, B1, K, Z (scalars = h, straight from computeH's device buffer), B2
-// enqueued back to back -> one synchronisation -> host: Horner per MSM, then
+// -> computeH -> MSM B2, Z (scalars = h, straight from computeH's device buffer), A, B1, K enqueued
+// back to back (each MSM's bucket reduction runs on a second stream under the next MSM's
+// accumulation; r*delta, s*delta, -rs*delta, s*delta2 are computed on the host meanwhile)
+// -> one synchronisation -> host: Horner per MSM, then
 //   Ar  = A + alpha + r*delta
 //   Bs1 = B1 + beta + s*delta           Bs = B2 + beta2 + s*delta2
 //   Krs = K + Z + (-rs)*delta + s*Ar + r*Bs1
@@ -159,15 +161,30 @@ static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out
   return 0;
 }
 
+// The multiples of delta do not depend on any MSM result: prove_device computes them on the host
+// while the GPU is still working.
+struct DeltaMultiples {
+  G1Affine r_delta, s_delta, kr_delta;  // r*delta, s*delta, (-rs)*delta
+  G2Affine s_delta2;                    // s*delta2
+};
+
+static DeltaMultiples delta_multiples(const b200g16_pk* pk, const Fr& r, const Fr& s) {
+  DeltaMultiples m;
+  m.r_delta = host_scalar_mul_aff<Fp>(pk->delta, r);
+  m.s_delta = host_scalar_mul_aff<Fp>(pk->delta, s);
+  m.kr_delta = host_scalar_mul_aff<Fp>(pk->delta, Fr::neg(Fr::mul(r, s)));
+  m.s_delta2 = host_scalar_mul_aff<Fp2>(pk->delta2, s);
+  return m;
+}
+
 // Ar, Bs, Krs (and bs1) from the five complete MSM results.
-static void prove_finish_host(const b200g16_pk* pk, const G1Affine& A, const G1Affine& B1, const G1Affine& K,
-                              const G1Affine& Z, const G2Affine& B2, const Fr& r, const Fr& s, b200g16_proof* out) {
-  Fr kr = Fr::neg(Fr::mul(r, s));
-  G1Affine ar = host_sum<Fp>({A, pk->alpha, host_scalar_mul_aff<Fp>(pk->delta, r)});
-  G1Affine bs1 = host_sum<Fp>({B1, pk->beta, host_scalar_mul_aff<Fp>(pk->delta, s)});
-  G1Affine krs = host_sum<Fp>({K, Z, host_scalar_mul_aff<Fp>(pk->delta, kr), host_scalar_mul_aff<Fp>(ar, s),
-                               host_scalar_mul_aff<Fp>(bs1, r)});
-  G2Affine bs = host_sum<Fp2>({B2, pk->beta2, host_scalar_mul_aff<Fp2>(pk->delta2, s)});
+static void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, const G1Affine& A, const G1Affine& B1,
+                              const G1Affine& K, const G1Affine& Z, const G2Affine& B2, const Fr& r, const Fr& s,
+                              b200g16_proof* out) {
+  G1Affine ar = host_sum<Fp>({A, pk->alpha, dm.r_delta});
+  G1Affine bs1 = host_sum<Fp>({B1, pk->beta, dm.s_delta});
+  G1Affine krs = host_sum<Fp>({K, Z, dm.kr_delta, host_scalar_mul_aff<Fp>(ar, s), host_scalar_mul_aff<Fp>(bs1, r)});
+  G2Affine bs = host_sum<Fp2>({B2, pk->beta2, dm.s_delta2});
   memcpy(out->ar, &ar, 64);
   memcpy(out->bs, &bs, 128);
   memcpy(out->krs, &krs, 64);
@@ -198,7 +215,10 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   MsmCfg cfg[5];
   const Fr* scal[5] = {sv[0], sv[1], sv[2], d_a + pk->off_z, sv[1]};
   const size_t cnt[5] = {pk->n_idx[0], pk->n_idx[1], pk->n_idx[2], pk->n_z, pk->n_idx[1]};
-  for (int i = 0; i < 5; i++) {
+  // G2 first: its bucket reduction is the longest tail and hides behind the four G1 MSMs that follow
+  const int order[5] = {4, 3, 0, 1, 2};
+  for (int k = 0; k < 5; k++) {
+    const int i = order[k];
     MsmTable tab;
     const MsmTable* tp = nullptr;
     if (i < 4) {
@@ -211,6 +231,8 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
     mark();
   }
   B200_TRY(msm_join(ctx));
+  DeltaMultiples dm;
+  if (!pk->partial) dm = delta_multiples(pk, r, s);  // host work hidden behind the GPU's
   B200_CUDA(cudaStreamSynchronize(st));
   *ev_io = ev;
 
@@ -224,7 +246,7 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
 
   memset(out, 0, sizeof(*out));
   if (!pk->partial) {
-    prove_finish_host(pk, A, B1, K, Z, B2, r, s, out);
+    prove_finish_host(pk, dm, A, B1, K, Z, B2, r, s, out);
   }
   memcpy(out->msm_a, &A, 64);
   memcpy(out->msm_b1, &B1, 64);
@@ -290,7 +312,7 @@ int b200g16_prove_finish(const b200g16_pk* pk, const uint64_t msm_a[8], const ui
   memcpy(&A, msm_a, 64); memcpy(&B1, msm_b1, 64); memcpy(&K, msm_k, 64); memcpy(&Z, msm_z, 64);
   memcpy(&B2, msm_b2, 128); memcpy(&fr_r, r, 32); memcpy(&fr_s, s, 32);
   memset(proof_out, 0, sizeof(*proof_out));
-  prove_finish_host(pk, A, B1, K, Z, B2, fr_r, fr_s, proof_out);
+  prove_finish_host(pk, delta_multiples(pk, fr_r, fr_s), A, B1, K, Z, B2, fr_r, fr_s, proof_out);
   memcpy(proof_out->msm_a, msm_a, 64); memcpy(proof_out->msm_b1, msm_b1, 64); memcpy(proof_out->msm_k, msm_k, 64);
   memcpy(proof_out->msm_z, msm_z, 64); memcpy(proof_out->msm_b2, msm_b2, 128);
   return 0;
