@@ -422,7 +422,12 @@ def run_prove_workload(args, rank, local_rank, world):
 
     def step():
         aa, bb, cc = a.clone(), b.clone(), c.clone()        # computeH works in place
-        part = ctx.prove_dev(pk, wires.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
+        if world == 1 or args.replicated_h:
+            part = ctx.prove_dev(pk, wires.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
+        else:       # a, b, c transformed on three ranks, broadcast, finished everywhere
+            torch.cuda.synchronize()                        # clones (torch stream) before the library's stream
+            sharded.compute_h_distributed(ctx, aa, bb, cc, L)
+            part = ctx.prove_h_dev(pk, wires.data_ptr(), aa.data_ptr(), rr, ss)
         if world == 1:
             return part
         t = torch.from_numpy(sharded.pack_partials(part).view(np.int64).copy()).to(dev)
@@ -462,7 +467,10 @@ def run_prove_workload(args, rank, local_rank, world):
             "config": {"workload": f"synthetic Groth16 prove, 2^{L} constraints, {N} wires, witness 40% 0/1 / 30% bytes / "
                                    f"30% uniform (SURVEY §8d config 1/5), inputs resident in HBM",
                        "window_tables": bool(args.table),
-                       "parallelism": f"pk point-range shards x{world}; computeH replicated; all_gather of 5 partial points"},
+                       "parallelism": f"pk point-range shards x{world}; computeH " +
+                                      ("replicated" if (world == 1 or args.replicated_h) else
+                                       "spread over 3 ranks (a, b, c) + 3 NCCL broadcasts") +
+                                      "; all_gather of 5 partial points"},
             "gpu_launches": launches,
             "phases_ms_rank0[h2d,gather,computeH,msmB2,msmZ,msmA,msmB1,msmK]": [round(x, 3) for x in ph],
             "proof_krs_limb0": int(res["krs"][0])}))
@@ -489,6 +497,8 @@ def main():
     ap.add_argument("--prove-logn", type=int, default=20)
     ap.add_argument("--no-table", dest="table", action="store_false",
                     help="run the MSM without the window table over the resident bases (b200g16_bases_precompute)")
+    ap.add_argument("--replicated-h", action="store_true",
+                    help="prove workload, N>1: every rank runs the whole computeH instead of spreading it over 3 ranks")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-traffic", type=float, default=None,

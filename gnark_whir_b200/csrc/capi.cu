@@ -19,6 +19,7 @@ int modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, dou
 int pipe_probe(b200g16_ctx* ctx, int mode, int blocks_per_sm, int iters, double* ops_per_s, float* ms_out);
 int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation);
 int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
+int h_pointwise_device(b200g16_ctx* ctx, Fr* a, const Fr* b, const Fr* c, int L);
 int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n);
 int sponge_batch_device(b200g16_ctx* ctx, const uint8_t* d_in, size_t in_len, size_t n, uint8_t* d_out, size_t out_len);
 int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_len, const uint64_t* d_sib,
@@ -391,6 +392,17 @@ int b200g16_compute_h_dev(b200g16_ctx* ctx, void* d_a, void* d_b, void* d_c, uns
   B200_CUDA(cudaSetDevice(ctx->device));
   return compute_h_device(ctx, reinterpret_cast<Fr*>(d_a), reinterpret_cast<Fr*>(d_b), reinterpret_cast<Fr*>(d_c),
                           (int)log2n, true);
+}
+
+int b200g16_h_pointwise_dev(b200g16_ctx* ctx, void* d_a, const void* d_b, const void* d_c, unsigned log2n) {
+  if (!ctx || !d_a || !d_b || !d_c) return fail(B200G16_ERR_ARG, "h_pointwise: null");
+  if (log2n > 28) return fail(B200G16_ERR_ARG, "h_pointwise: log2n=%u exceeds two-adicity 28", log2n);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(h_pointwise_device(ctx, reinterpret_cast<Fr*>(d_a), reinterpret_cast<const Fr*>(d_b),
+                              reinterpret_cast<const Fr*>(d_c), (int)log2n));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,

@@ -77,7 +77,9 @@ __device__ __forceinline__ Fr twiddle(const Fr* __restrict__ tw, uint32_t e, int
 }
 
 struct NttPassArgs {
-  Fr* data;
+  Fr* data;         // blockIdx.y-th vector = vecs[y] when nvecs > 0, else data + y * 2^L
+  Fr* vecs[3];
+  int nvecs;
   const Fr* tw;
   const Fr* pre;    // multiply on load by pre[idx]  (nullptr = none)
   const Fr* post;   // multiply on store by post[idx] (nullptr = none)
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
   SmemTile sm{reinterpret_cast<uint4*>(smem_raw), reinterpret_cast<uint4*>(smem_raw) + T};
   const uint32_t lowmask = (1u << b0) - 1u;
   const uint32_t tile = blockIdx.x;
-  Fr* data = A.data + (size_t)blockIdx.y * ((size_t)1 << L);  // batched transforms
+  Fr* data = A.nvecs ? A.vecs[blockIdx.y] : A.data + (size_t)blockIdx.y * ((size_t)1 << L);  // batched transforms
 
   // ---- load
   for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
@@ -129,11 +131,16 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
       uint32_t t1 = t0 | (1u << lb);
       uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
       uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
+      Fr xv = sm.get(s0), yv = sm.get(s1);
+      if (pb == 0) {  // the level whose twiddles are all w^0 = 1: no products (warp-uniform branch)
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::sub(xv, yv));
+        continue;
+      }
       uint32_t u = (tile << logc) + c;
       uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
       uint32_t e = j << (L - 1 - pb);
       Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
-      Fr xv = sm.get(s0), yv = sm.get(s1);
       if (DIT) {
         yv = Fr::mul(yv, w);
         sm.put(s0, Fr::add(xv, yv));
@@ -257,8 +264,10 @@ static int ensure_coset(b200g16_ctx* ctx, int L) {
   return 0;
 }
 
-// In-place transform of `batch` consecutive vectors of 2^L elements at d_data.
-int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation) {
+// In-place transform of `batch` vectors of 2^L elements: consecutive at d_data, or (vecs != nullptr,
+// batch <= 3) at vecs[0..batch) — computeH transforms a, b, c in one launch per pass.
+static int ntt_device_impl(b200g16_ctx* ctx, Fr* d_data, Fr* const* vecs, int L, int batch, bool inverse, bool coset,
+                           int decimation) {
   if (L < 0 || L > 28) return fail(B200G16_ERR_ARG, "ntt: log2n=%d out of range (two-adicity 28)", L);
   if (decimation != B200G16_DIF && decimation != B200G16_DIT) return fail(B200G16_ERR_ARG, "ntt: bad decimation");
   if (batch < 1) return fail(B200G16_ERR_ARG, "ntt: batch");
@@ -272,6 +281,8 @@ int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, boo
 
   NttPassArgs A;
   A.data = d_data;
+  A.nvecs = vecs ? batch : 0;
+  for (int i = 0; i < 3; i++) A.vecs[i] = (vecs && i < batch) ? vecs[i] : nullptr;
   A.tw = ws.tw.as<Fr>();
   A.tw_sh = ws.tw_log - L;
   A.tw_half = (uint32_t)(((size_t)1 << ws.tw_log) >> 1);
@@ -332,6 +343,24 @@ int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, boo
   return 0;
 }
 
+int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation) {
+  return ntt_device_impl(ctx, d_data, nullptr, L, batch, inverse, coset, decimation);
+}
+
+static Fr coset_denominator_inv(size_t n) {  // 1 / (g^N - 1)
+  const uint32_t g[8] = B200_FR_GEN;
+  return Fr::inv(Fr::sub(fr_pow_u64(fr_from_limbs(g), (uint64_t)n), Fr::one()));
+}
+
+// computeH's pointwise step on coset evaluations: a = (a * b - c) / (g^N - 1)
+int h_pointwise_device(b200g16_ctx* ctx, Fr* a, const Fr* b, const Fr* c, int L) {
+  const size_t n = (size_t)1 << L;
+  k_h_pointwise<<<cdiv_u(n, 256), 256, 0, ctx->stream>>>(a, b, c, (uint32_t)n, coset_denominator_inv(n));
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // computeH on device buffers a,b,c (each 2^L elements, already zero-padded); result in a.
 int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time) {
   const size_t n = (size_t)1 << L;
@@ -342,14 +371,11 @@ int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and
   B200_TRY(ensure_coset(ctx, L));
   mark();
   Fr* v[3] = {a, b, c};
-  for (int i = 0; i < 3; i++) B200_TRY(ntt_device(ctx, v[i], L, 1, true, false, B200G16_DIF));
+  B200_TRY(ntt_device_impl(ctx, nullptr, v, L, 3, true, false, B200G16_DIF));
   mark();
-  for (int i = 0; i < 3; i++) B200_TRY(ntt_device(ctx, v[i], L, 1, false, true, B200G16_DIT));
+  B200_TRY(ntt_device_impl(ctx, nullptr, v, L, 3, false, true, B200G16_DIT));
   mark();
-  const uint32_t g[8] = B200_FR_GEN;
-  Fr den = Fr::inv(Fr::sub(fr_pow_u64(fr_from_limbs(g), (uint64_t)n), Fr::one()));
-  k_h_pointwise<<<cdiv_u(n, 256), 256, 0, ctx->stream>>>(a, b, c, (uint32_t)n, den);
-  ctx->launches++;
+  B200_TRY(h_pointwise_device(ctx, a, b, c, L));
   mark();
   B200_TRY(ntt_device(ctx, a, L, 1, true, true, B200G16_DIF));
   mark();

@@ -192,6 +192,7 @@ static void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, co
 }
 
 // d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
+// d_b == nullptr: d_a already holds h (computeH was done elsewhere, e.g. spread over several GPUs).
 static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, Fr* d_a, Fr* d_b, Fr* d_c,
                         const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io) {
   cudaStream_t st = ctx->stream;
@@ -210,7 +211,7 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
       ctx->launches++;
     }
   mark();
-  B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
+  if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
   mark();
   MsmCfg cfg[5];
   const Fr* scal[5] = {sv[0], sv[1], sv[2], d_a + pk->off_z, sv[1]};
@@ -315,6 +316,24 @@ int b200g16_prove_finish(const b200g16_pk* pk, const uint64_t msm_a[8], const ui
   prove_finish_host(pk, delta_multiples(pk, fr_r, fr_s), A, B1, K, Z, B2, fr_r, fr_s, proof_out);
   memcpy(proof_out->msm_a, msm_a, 64); memcpy(proof_out->msm_b1, msm_b1, 64); memcpy(proof_out->msm_k, msm_k, 64);
   memcpy(proof_out->msm_z, msm_z, 64); memcpy(proof_out->msm_b2, msm_b2, 128);
+  return 0;
+}
+
+int b200g16_prove_h_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_h, const uint64_t r[4],
+                        const uint64_t s[4], b200g16_proof* proof_out) {
+  if (!ctx || !pk || !d_wires || !d_h || !r || !s || !proof_out) return fail(B200G16_ERR_ARG, "prove_h_dev: null");
+  if (pk->device != ctx->device) return fail(B200G16_ERR_STATE, "prove_h_dev: pk lives on another device");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  int ev = 0;
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  Fr fr_r, fr_s;
+  memcpy(&fr_r, r, 32);
+  memcpy(&fr_s, s, 32);
+  B200_TRY(prove_device(ctx, pk, (const Fr*)d_wires, (Fr*)d_h, nullptr, nullptr, fr_r, fr_s, proof_out, &ev));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   return 0;
 }
 

@@ -67,6 +67,8 @@ SIGNATURES = {
     "b200g16_pk_free": (None, [_vp]),
     "b200g16_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "b200g16_prove_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200g16_prove_h_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200g16_h_pointwise_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint]),
     "b200g16_prove_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_pairing_check": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
     "b200g16_pair": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -439,6 +441,16 @@ class Context:
         c, w = C.c_int(), C.c_int()
         _check(load().b200g16_msm_plan(self.h, bases.handle, bases.n if n is None else n, C.byref(c), C.byref(w)))
         return c.value, w.value
+
+    def h_pointwise_dev(self, d_a, d_b, d_c, log2n):
+        _check(load().b200g16_h_pointwise_dev(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)), log2n))
+
+    def prove_h_dev(self, pk, d_wires, d_h, r, s):
+        """prove_dev with h already computed (d_h: N elements, bit-reversed order)."""
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        out = ProofOut()
+        _check(load().b200g16_prove_h_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
+        return out.as_dict()
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
     def msm(self, bases, scalars, offset=0, n=None):

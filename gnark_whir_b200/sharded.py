@@ -104,6 +104,41 @@ def prove_sharded(ctx, pk_shard, wires, a, b, c, r, s, device=None, pg=None):
     return ctx.prove_finish(pk_shard, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], r, s)
 
 
+def h_vector_owner(v, world):
+    """Rank that transforms vector v (0 = a, 1 = b, 2 = c) in compute_h_distributed."""
+    return v % min(world, 3)
+
+
+def compute_h_distributed(ctx, t_a, t_b, t_c, log2n, pg=None):
+    """computeH spread over the ranks of a process group.  t_a, t_b, t_c: torch int64 tensors (N, 4) on
+    this rank's GPU holding the same zero-padded a, b, c on every rank; h is left in t_a on every rank.
+
+    gnark runs the FFTInverse + coset-FFT pairs of a, b and c in three goroutines; here up to three
+    ranks take one vector each (2 of the 7 transforms), broadcast the coset evaluations over NCCL /
+    NVLink (N x 32 B each), and every rank finishes with the pointwise step and the last transform.
+    Critical path: 2 + 1 transforms + 3 broadcasts instead of 7 transforms.  The result is the same
+    field elements in the same order as b200g16_compute_h_dev (bit-exact; tests/test_sharded_cpu.py
+    checks the orchestration over gloo, tests/test_gpu_prove.py the arithmetic)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(pg) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        ctx.compute_h_dev(t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr(), log2n)
+        return t_a
+    rank = dist.get_rank(pg)
+    vecs = (t_a, t_b, t_c)
+    for v, t in enumerate(vecs):
+        if h_vector_owner(v, world) == rank:
+            ctx.ntt_dev(t.data_ptr(), log2n, inverse=True, decimation=lib.DIF)
+            ctx.ntt_dev(t.data_ptr(), log2n, coset=True, decimation=lib.DIT)
+    for v, t in enumerate(vecs):
+        src = h_vector_owner(v, world)
+        dist.broadcast(t, src=dist.get_global_rank(pg, src) if pg is not None else src, group=pg)
+    ctx.h_pointwise_dev(t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr(), log2n)
+    ctx.ntt_dev(t_a.data_ptr(), log2n, inverse=True, coset=True, decimation=lib.DIF)
+    return t_a
+
+
 class ShardedBases:
     """This rank's slice of a point vector, resident on this rank's GPU."""
 

@@ -211,6 +211,13 @@ int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, co
 /* Same on zero-padded DEVICE vectors of N elements; h overwrites d_a (b, c are clobbered). */
 int b200g16_compute_h_dev(b200g16_ctx* ctx, void* d_a, void* d_b, void* d_c, unsigned log2n);
 
+/* computeH split into its stages, for spreading it over several GPUs (gnark runs the three
+ * FFTInverse / coset-FFT pairs of a, b, c in three goroutines; here three ranks each take one
+ * vector through b200g16_ntt_dev(inverse, DIF) + b200g16_ntt_dev(coset, DIT), broadcast it, and
+ * every rank finishes with this pointwise step + b200g16_ntt_dev(inverse, coset, DIF)):
+ * d_a[i] = (d_a[i] * d_b[i] - d_c[i]) / (g^N - 1) on N = 2^log2n coset evaluations. */
+int b200g16_h_pointwise_dev(b200g16_ctx* ctx, void* d_a, const void* d_b, const void* d_c, unsigned log2n);
+
 /* ---- batched Keccak-f[1600] / duplex sponge / Merkle paths ---------------------------- */
 /* Permute n independent 200-byte states (25 little-endian u64 lanes, lane = x + 5y) in
  * place.  Replaces gnark std/permutation/keccakf.Permute as called from the reference's
@@ -312,6 +319,11 @@ int b200g16_pair(b200g16_ctx* ctx, const uint64_t* g1_points, const uint64_t* g2
 int b200g16_verify(b200g16_ctx* ctx, const b200g16_vk_desc* vk, const uint64_t ar[8], const uint64_t bs[16],
                    const uint64_t krs[8], const uint64_t* commitment, const uint64_t* commitment_pok,
                    const uint64_t* public_inputs, size_t n_public, int* ok_out);
+
+/* b200g16_prove_dev with computeH already done: d_h holds h (N elements, bit-reversed order, as
+ * b200g16_compute_h_dev leaves it in d_a). */
+int b200g16_prove_h_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_h,
+                        const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out);
 
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */

@@ -127,6 +127,43 @@ def test_prove_with_window_tables_is_identical(ctx):
         pk.free()
 
 
+def test_staged_compute_h_and_prove_h_match_prove(ctx):
+    """The multi-GPU prove runs computeH as separate stages (b200g16_ntt_dev x2 per vector on three ranks,
+    broadcast, b200g16_h_pointwise_dev, last transform) and then b200g16_prove_h_dev: on one GPU the stages
+    must reproduce b200g16_compute_h / b200g16_prove bit for bit."""
+    import torch
+    from gnark_whir_b200 import lib, sharded
+    r1cs, w, tw, r, s = _case(123, 200, 3, False)
+    pk, _ = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        a, b, c = g16.solve_abc(r1cs, w)
+        L, N = pk.log2_domain, 1 << pk.log2_domain
+        fr = [g16.fr_array(w), g16.fr_array(a), g16.fr_array(b), g16.fr_array(c), g16.fr_array([r])[0], g16.fr_array([s])[0]]
+        full, h = ctx.prove(pk.device_handle(ctx), *fr, want_h=True, log2_domain=L)
+
+        def dev(x):
+            t = torch.zeros((N, 4), dtype=torch.int64, device="cuda")
+            t[:x.shape[0]] = torch.from_numpy(x.view(np.int64)).cuda()
+            return t
+        ta, tb, tc = dev(fr[1]), dev(fr[2]), dev(fr[3])
+        for t in (ta, tb, tc):
+            ctx.ntt_dev(t.data_ptr(), L, inverse=True, decimation=lib.DIF)
+            ctx.ntt_dev(t.data_ptr(), L, coset=True, decimation=lib.DIT)
+        ctx.h_pointwise_dev(ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), L)
+        ctx.ntt_dev(ta.data_ptr(), L, inverse=True, coset=True, decimation=lib.DIF)
+        assert np.array_equal(ta.cpu().numpy().view(np.uint64), h)
+        # world of one: compute_h_distributed is the plain library call
+        ta2, tb2, tc2 = dev(fr[1]), dev(fr[2]), dev(fr[3])
+        sharded.compute_h_distributed(ctx, ta2, tb2, tc2, L)
+        assert torch.equal(ta, ta2)
+        wires = torch.from_numpy(fr[0].view(np.int64)).cuda()
+        staged = ctx.prove_h_dev(pk.device_handle(ctx), wires.data_ptr(), ta.data_ptr(), fr[4], fr[5])
+        for k in full:
+            assert np.array_equal(full[k], staged[k]), k
+    finally:
+        pk.free()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_prove_equals_single_gpu_prove(ctx, world):
     """Point-range shards of the proving key (config 5): the shards' partial MSM sums, added and

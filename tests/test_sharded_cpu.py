@@ -70,3 +70,71 @@ def test_two_rank_gloo_exchange_and_combine():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+# ---- computeH spread over ranks (sharded.compute_h_distributed): orchestration over gloo, with the C oracle
+# standing in for the per-GPU transforms
+class _OracleCtx:
+    """Duck-types the three lib.Context calls compute_h_distributed makes, on CPU tensors."""
+
+    def __init__(self):
+        self.t = {}
+
+    def reg(self, *tensors):
+        for t in tensors:
+            self.t[t.data_ptr()] = t
+
+    def _arr(self, ptr):
+        return self.t[ptr].numpy().view(np.uint64)
+
+    def ntt_dev(self, ptr, log2n, batch=1, inverse=False, coset=False, decimation=0):
+        from oracle import cport
+        a = self._arr(ptr)
+        a[:] = cport.ntt(a, inverse=inverse, coset=coset, decimation=decimation)
+
+    def h_pointwise_dev(self, pa, pb, pc, log2n):
+        a, b, c = (bn.fr_from_mont_array(self._arr(p)) for p in (pa, pb, pc))
+        den = pow(pow(5, 1 << log2n, R) - 1, -1, R)
+        self._arr(pa)[:] = bn.fr_to_mont_array([(x * y - z) * den % R for x, y, z in zip(a, b, c)])
+
+
+def _h_worker(rank, world, port, logn, q):
+    import random
+
+    import torch
+    import torch.distributed as dist
+    from oracle import cport
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = random.Random(7)                                    # same inputs on every rank
+    n = 1 << logn
+    a, b, c = ([rng.randrange(R) for _ in range(n)] for _ in range(3))
+    arrs = [bn.fr_to_mont_array(v) for v in (a, b, c)]
+    exp = cport.compute_h(arrs[0], arrs[1], arrs[2], logn)
+    ts = [torch.from_numpy(x.view(np.int64).copy()) for x in arrs]
+    ctx = _OracleCtx()
+    ctx.reg(*ts)
+    h = sharded.compute_h_distributed(ctx, ts[0], ts[1], ts[2], logn)
+    q.put((rank, bool(np.array_equal(h.numpy().view(np.uint64), exp))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_compute_h_distributed_over_gloo(world):
+    assert [sharded.h_vector_owner(v, 8) for v in range(3)] == [0, 1, 2]
+    assert [sharded.h_vector_owner(v, 2) for v in range(3)] == [0, 1, 0]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_h_worker, args=(r, world, port, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(r, True) for r in range(world)]
