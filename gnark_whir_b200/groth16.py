@@ -165,6 +165,36 @@ class Proof:                       # groth16_bn254.Proof
     debug: dict = field(default_factory=dict)   # intermediate MSM outputs, h (parity checks)
 
 
+def proof_write_to(ctx, proof, raw=False):
+    """(*Proof).WriteTo (raw=False, compressed points) / WriteRawTo (raw=True) -> bytes:
+    Ar | Bs | Krs | uint32 len(Commitments) | Commitments... | CommitmentPok
+    (gnark backend/groth16/bn254/marshal.go; point encodings by b200g16_g1/g2_encode)."""
+    pok = proof.CommitmentPok if proof.CommitmentPok is not None else np.zeros(8, dtype=np.uint64)
+    g1 = np.stack([np.asarray(p, dtype=np.uint64).reshape(8) for p in [proof.Ar, proof.Krs, *proof.Commitments, pok]])
+    e1 = ctx.encode_points(g1, group=1, raw=raw)
+    e2 = ctx.encode_points(np.asarray(proof.Bs, dtype=np.uint64).reshape(1, 16), group=2, raw=raw)
+    k = len(proof.Commitments)
+    return (e1[0].tobytes() + e2[0].tobytes() + e1[1].tobytes() + k.to_bytes(4, "big")
+            + b"".join(e1[2 + i].tobytes() for i in range(k)) + e1[2 + k].tobytes())
+
+
+def proof_read_from(ctx, data, raw=False):
+    """(*Proof).ReadFrom -> Proof; raises ValueError on an invalid encoding (gnark returns the decoder's error)."""
+    s1, s2 = (64, 128) if raw else (32, 64)
+    o = 2 * s1 + s2
+    if len(data) < o + 4:
+        raise ValueError("groth16.Proof.ReadFrom: short buffer")
+    k = int.from_bytes(data[o:o + 4], "big")
+    if len(data) < o + 4 + (k + 1) * s1:
+        raise ValueError("groth16.Proof.ReadFrom: short buffer")
+    g1_bytes = data[:s1] + data[s1 + s2:o] + data[o + 4:o + 4 + (k + 1) * s1]
+    g1, ok1 = ctx.decode_points(g1_bytes, group=1, raw=raw)
+    g2, ok2 = ctx.decode_points(data[s1:s1 + s2], group=2, raw=raw)
+    if not (ok1.all() and ok2.all()):
+        raise ValueError("groth16.Proof.ReadFrom: invalid point encoding")
+    return Proof(g1[0], g1[1], g2[0], [g1[2 + i] for i in range(k)], g1[2 + k])
+
+
 @dataclass
 class ToxicWaste:
     tau: int

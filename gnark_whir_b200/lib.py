@@ -73,6 +73,10 @@ SIGNATURES = {
     "b200g16_pairing_check": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
     "b200g16_pair": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "b200g16_verify": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
+    "b200g16_g1_decode": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp]),
+    "b200g16_g2_decode": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp]),
+    "b200g16_g1_encode": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp]),
+    "b200g16_g2_encode": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -435,6 +439,30 @@ class Context:
                                      _ptr(opt[3]) if opt[3] is not None else None,
                                      _ptr(pub) if pub.shape[0] else None, pub.shape[0], C.byref(ok)))
         return bool(ok.value)
+
+    # -- gnark-crypto point encodings (G1Affine.Bytes / RawBytes / SetBytes and the G2 counterparts)
+    def encode_points(self, points, group=1, raw=False):
+        """points (n, 8|16) uint64 -> (n, record) uint8, record = 32|64 compressed, 64|128 raw"""
+        pts = _u64(points, 8 if group == 1 else 16)
+        rec = (32 if group == 1 else 64) * (2 if raw else 1)
+        out = np.zeros((pts.shape[0], rec), dtype=np.uint8)
+        fn = load().b200g16_g1_encode if group == 1 else load().b200g16_g2_encode
+        _check(fn(self.h, _ptr(pts), pts.shape[0], int(raw), _ptr(out)))
+        return out
+
+    def decode_points(self, data, group=1, raw=False, subgroup_check=True):
+        """data: bytes / uint8 array of n fixed-size records -> (points (n, 8|16) uint64, ok (n,) bool)"""
+        rec = (32 if group == 1 else 64) * (2 if raw else 1)
+        buf = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray))
+                                   else data, dtype=np.uint8).reshape(-1, rec)
+        n = buf.shape[0]
+        out = np.zeros((n, 8 if group == 1 else 16), dtype=np.uint64)
+        ok = np.zeros(n, dtype=np.uint8)
+        if group == 1:
+            _check(load().b200g16_g1_decode(self.h, _ptr(buf), n, int(raw), _ptr(out), _ptr(ok)))
+        else:
+            _check(load().b200g16_g2_decode(self.h, _ptr(buf), n, int(raw), int(subgroup_check), _ptr(out), _ptr(ok)))
+        return out, ok.astype(bool)
 
     def msm_plan(self, bases, n=None):
         """(window bits c, digits per scalar W) the library uses for an n-point MSM on `bases`."""

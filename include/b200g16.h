@@ -325,6 +325,23 @@ int b200g16_verify(b200g16_ctx* ctx, const b200g16_vk_desc* vk, const uint64_t a
 int b200g16_prove_h_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires, void* d_h,
                         const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out);
 
+/* ---- gnark wire formats: point encodings, batched ---------------------------------------- */
+/* gnark-crypto ecc/bn254/marshal.go, applied element by element by the curve Encoder / Decoder to the
+ * point slices of groth16_bn254.ProvingKey / VerifyingKey / Proof (gnark backend/groth16/bn254/
+ * marshal.go WriteTo / WriteRawTo / ReadFrom).  Big-endian field elements, two flag bits on top of the
+ * first byte: 0b00 uncompressed, 0b01 infinity, 0b10 / 0b11 compressed with the lexicographically
+ * smallest / largest Y; G2 writes X.A1 before X.A0.  Fixed-size records: raw = 0 -> compressed
+ * (G1 32 B, G2 64 B: G1Affine.Bytes / SetBytes), raw = 1 -> uncompressed (64 / 128 B: RawBytes).
+ * decode: ok_out[i] = 1 for a valid encoding of a curve point (and, for G2 with subgroup_check, a
+ * point of the r-torsion subgroup, as the Decoder checks by default); invalid records decode to
+ * infinity with ok_out[i] = 0.  Reading a compressed key costs one square root per point, which is
+ * why this runs on the GPU.  Host pointers. */
+int b200g16_g1_decode(b200g16_ctx* ctx, const uint8_t* in, size_t n, int raw, uint64_t* out_points, uint8_t* ok_out);
+int b200g16_g2_decode(b200g16_ctx* ctx, const uint8_t* in, size_t n, int raw, int subgroup_check,
+                      uint64_t* out_points, uint8_t* ok_out);
+int b200g16_g1_encode(b200g16_ctx* ctx, const uint64_t* points, size_t n, int raw, uint8_t* out);
+int b200g16_g2_encode(b200g16_ctx* ctx, const uint64_t* points, size_t n, int raw, uint8_t* out);
+
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);

@@ -1,0 +1,169 @@
+"""TEST ORACLE (not product code): gnark-crypto / gnark wire formats for BN254, restated in python big ints.
+
+Follows (recalled, sources absent from /root/reference — go.mod:6-7 pins the modules):
+  gnark-crypto ecc/bn254/marshal.go   G1Affine.Bytes / RawBytes / SetBytes, G2Affine likewise, Encoder slices
+  gnark backend/groth16/bn254/marshal.go   Proof.WriteTo / WriteRawTo / ReadFrom
+reached from the reference when a proof leaves the process (mt.go:496-497 keep it in memory; ProveKit-side
+tooling serialises it).
+
+Point encodings (big-endian field elements, 2 flag bits in the most significant bits of the first byte):
+  0b00 uncompressed (X || Y)         0b01 point at infinity (rest zero; compressed or uncompressed length)
+  0b10 compressed, Y is the lexicographically smallest root        0b11 compressed, Y the largest
+G1: X is 32 bytes.  G2: X = X.A1 || X.A0 (64 bytes), Y likewise; "largest" compares A1 first, then A0.
+Slices: uint32 big-endian length, then the elements.
+Proof: Ar (G1) | Bs (G2) | Krs (G1) | len(Commitments) u32 | Commitments... (G1) | CommitmentPok (G1).
+Parity is UNPINNED by the reference (no vectors on disk); pins here are algebraic (round trips, on-curve,
+sign rule) — see tests/test_oracle_cpu.py.
+"""
+from . import bn254 as bn
+from .bn254 import P
+
+M_UNCOMPRESSED, M_INFINITY, M_SMALLEST, M_LARGEST = 0x00, 0x40, 0x80, 0xC0
+HALF = (P - 1) // 2
+
+
+def fp_lex_largest(y):
+    return y > HALF
+
+
+def fp2_lex_largest(y):
+    return y[1] > HALF if y[1] != 0 else y[0] > HALF
+
+
+def fp_sqrt(a):
+    r = pow(a, (P + 1) // 4, P)
+    return r if r * r % P == a % P else None
+
+
+def fp2_sqrt(a):
+    """complex method, p = 3 mod 4; None if a is not a square"""
+    a0, a1 = a[0] % P, a[1] % P
+    if a1 == 0:
+        r = fp_sqrt(a0)
+        if r is not None:
+            return (r, 0)
+        r = fp_sqrt(-a0 % P)
+        return None if r is None else (0, r)
+    s = fp_sqrt((a0 * a0 + a1 * a1) % P)
+    if s is None:
+        return None
+    inv2 = pow(2, -1, P)
+    t = (a0 + s) * inv2 % P
+    x0 = fp_sqrt(t)
+    if x0 is None:
+        t = (a0 - s) * inv2 % P
+        x0 = fp_sqrt(t)
+        if x0 is None:
+            return None
+    x1 = a1 * pow(2 * x0, -1, P) % P
+    return (x0, x1) if bn.f2_sqr((x0, x1)) == (a0, a1) else None
+
+
+# ---------------------------------------------------------------- G1
+def g1_bytes(pt):
+    """G1Affine.Bytes(): 32 bytes compressed"""
+    if pt is None:
+        return bytes([M_INFINITY]) + bytes(31)
+    b = bytearray(pt[0].to_bytes(32, "big"))
+    b[0] |= M_LARGEST if fp_lex_largest(pt[1]) else M_SMALLEST
+    return bytes(b)
+
+
+def g1_raw_bytes(pt):
+    """G1Affine.RawBytes() / Marshal(): 64 bytes uncompressed"""
+    if pt is None:
+        return bytes([M_INFINITY]) + bytes(63)
+    return pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
+
+
+def g1_set_bytes(buf):
+    """G1Affine.SetBytes: -> (point, bytes consumed); raises ValueError on an invalid encoding"""
+    flag = buf[0] & 0xC0
+    if flag == M_INFINITY:
+        n = 32  # gnark-crypto consumes the compressed size for a compressed-infinity marker
+        if any(buf[1:32]) or buf[0] & 0x3F:
+            raise ValueError("invalid infinity encoding")
+        return None, n
+    if flag == M_UNCOMPRESSED:
+        x, y = int.from_bytes(buf[:32], "big"), int.from_bytes(buf[32:64], "big")
+        if x >= P or y >= P or not bn.g1_on_curve((x, y)):
+            raise ValueError("invalid point")
+        return (x, y), 64
+    x = int.from_bytes(bytes([buf[0] & 0x3F]) + bytes(buf[1:32]), "big")
+    if x >= P:
+        raise ValueError("x not reduced")
+    y = fp_sqrt((x * x * x + 3) % P)
+    if y is None:
+        raise ValueError("x is not on the curve")
+    if fp_lex_largest(y) != (flag == M_LARGEST):
+        y = P - y
+    return (x, y), 32
+
+
+# ---------------------------------------------------------------- G2
+def g2_bytes(pt):
+    if pt is None:
+        return bytes([M_INFINITY]) + bytes(63)
+    (x0, x1), y = pt
+    b = bytearray(x1.to_bytes(32, "big") + x0.to_bytes(32, "big"))
+    b[0] |= M_LARGEST if fp2_lex_largest(y) else M_SMALLEST
+    return bytes(b)
+
+
+def g2_raw_bytes(pt):
+    if pt is None:
+        return bytes([M_INFINITY]) + bytes(127)
+    (x0, x1), (y0, y1) = pt
+    return b"".join(v.to_bytes(32, "big") for v in (x1, x0, y1, y0))
+
+
+def g2_set_bytes(buf, subgroup_check=True):
+    flag = buf[0] & 0xC0
+    if flag == M_INFINITY:
+        if any(buf[1:64]) or buf[0] & 0x3F:
+            raise ValueError("invalid infinity encoding")
+        return None, 64
+    if flag == M_UNCOMPRESSED:
+        x1, x0, y1, y0 = (int.from_bytes(buf[32 * i:32 * i + 32], "big") for i in range(4))
+        pt = ((x0, x1), (y0, y1))
+        if max(x0, x1, y0, y1) >= P or not bn.g2_on_curve(pt):
+            raise ValueError("invalid point")
+        n = 128
+    else:
+        x1 = int.from_bytes(bytes([buf[0] & 0x3F]) + bytes(buf[1:32]), "big")
+        x0 = int.from_bytes(buf[32:64], "big")
+        if x0 >= P or x1 >= P:
+            raise ValueError("x not reduced")
+        x = (x0, x1)
+        y = fp2_sqrt(bn.f2_add(bn.f2_mul(bn.f2_sqr(x), x), bn.B2))
+        if y is None:
+            raise ValueError("x is not on the curve")
+        if fp2_lex_largest(y) != (flag == M_LARGEST):
+            y = bn.f2_neg(y)
+        pt, n = (x, y), 64
+    if subgroup_check and bn._mul(bn._F2, pt, bn.R, mod=1 << 300) is not None:
+        raise ValueError("point not in the r-torsion subgroup")
+    return pt, n
+
+
+# ---------------------------------------------------------------- groth16 Proof
+def proof_write(ar, bs, krs, commitments, pok, raw=False):
+    e1, e2 = (g1_raw_bytes, g2_raw_bytes) if raw else (g1_bytes, g2_bytes)
+    out = e1(ar) + e2(bs) + e1(krs) + len(commitments).to_bytes(4, "big")
+    for c in commitments:
+        out += e1(c)
+    return out + e1(pok)
+
+
+def proof_read(buf):
+    o = 0
+    ar, n = g1_set_bytes(buf[o:]); o += n
+    bs, n = g2_set_bytes(buf[o:]); o += n
+    krs, n = g1_set_bytes(buf[o:]); o += n
+    k = int.from_bytes(buf[o:o + 4], "big"); o += 4
+    coms = []
+    for _ in range(k):
+        c, n = g1_set_bytes(buf[o:]); o += n
+        coms.append(c)
+    pok, n = g1_set_bytes(buf[o:]); o += n
+    return ar, bs, krs, coms, pok, o

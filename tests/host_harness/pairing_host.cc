@@ -50,6 +50,18 @@ void host_f12_inv(const uint64_t* a, uint64_t* out) {
   Fp12 r = f12_inv(x);
   memcpy(out, &r, sizeof(r));
 }
+void host_f12_frob(const uint64_t* a, int k, uint64_t* out) {
+  Fp12 x;
+  memcpy(&x, a, sizeof(x));
+  Fp12 r = k == 1 ? f12_frob1(x) : (k == 2 ? f12_frob2(x) : f12_frob3(x));
+  memcpy(out, &r, sizeof(r));
+}
+void host_f12_sqr(const uint64_t* a, uint64_t* out) {
+  Fp12 x;
+  memcpy(&x, a, sizeof(x));
+  Fp12 r = f12_sqr(x);
+  memcpy(out, &r, sizeof(r));
+}
 void host_f12_frob2(const uint64_t* a, uint64_t* out) {
   Fp12 x;
   memcpy(&x, a, sizeof(x));

@@ -1,0 +1,105 @@
+"""GPU parity: gnark-crypto point encodings and the groth16 Proof wire format through the C-ABI
+(b200g16_g1/g2_encode, b200g16_g1/g2_decode; gnark_whir_b200.groth16.proof_write_to / proof_read_from)
+against the python restatement oracle/serialize.py.  Byte-exact both ways."""
+import random
+
+import numpy as np
+import pytest
+
+from gnark_whir_b200 import groth16 as g16
+from oracle import bn254 as bn
+from oracle import serialize as ser
+from oracle.bn254 import R
+
+pytestmark = pytest.mark.gpu
+
+
+def _points(rng, n):
+    g1 = [bn.g1_mul(bn.G1_GEN, rng.randrange(1, R)) for _ in range(n)]
+    g2 = [bn.g2_mul(bn.G2_GEN, rng.randrange(1, R)) for _ in range(n)]
+    g1 += [bn.g1_neg(p) for p in g1[:n // 2]] + [None, bn.G1_GEN]
+    g2 += [bn.g2_neg(p) for p in g2[:n // 2]] + [None, bn.G2_GEN]
+    return g1, g2
+
+
+@pytest.mark.parametrize("raw", [False, True])
+def test_encode_decode_match_oracle(ctx, raw):
+    rng = random.Random(41 + raw)
+    g1, g2 = _points(rng, 24)
+    e1 = ctx.encode_points(bn.g1_to_array(g1), group=1, raw=raw)
+    e2 = ctx.encode_points(bn.g2_to_array(g2), group=2, raw=raw)
+    o1 = [ser.g1_raw_bytes(p) if raw else ser.g1_bytes(p) for p in g1]
+    o2 = [ser.g2_raw_bytes(p) if raw else ser.g2_bytes(p) for p in g2]
+    assert [bytes(r) for r in e1] == o1
+    assert [bytes(r) for r in e2] == o2
+    d1, ok1 = ctx.decode_points(b"".join(o1), group=1, raw=raw)
+    d2, ok2 = ctx.decode_points(b"".join(o2), group=2, raw=raw)
+    assert ok1.all() and ok2.all()
+    assert np.array_equal(d1, bn.g1_to_array(g1)) and np.array_equal(d2, bn.g2_to_array(g2))
+
+
+def test_decode_rejects_invalid_records(ctx):
+    rng = random.Random(43)
+    good = ser.g1_bytes(bn.g1_mul(bn.G1_GEN, 7))
+    bad_x = next(bytes([0x80]) + x.to_bytes(31, "big") for x in range(2, 200)
+                 if ser.fp_sqrt((x ** 3 + 3) % bn.P) is None)                    # x^3 + 3 not a square
+    too_big = bytes([0xBF]) + bytes([0xFF] * 31)                                  # x >= p
+    bad_inf = bytes([0x40]) + bytes(30) + bytes([1])                              # infinity flag with payload
+    uncompressed_in_compressed = bytes([0x00]) + bytes(31)
+    pts, ok = ctx.decode_points(good + bad_x + too_big + bad_inf + uncompressed_in_compressed, group=1)
+    assert list(ok) == [True, False, False, False, False]
+    assert not pts[1:].any()
+    # raw record that is not on the curve
+    p = bn.g1_mul(bn.G1_GEN, 9)
+    off = p[0].to_bytes(32, "big") + ((p[1] + 1) % bn.P).to_bytes(32, "big")
+    _, ok = ctx.decode_points(ser.g1_raw_bytes(p) + off, group=1, raw=True)
+    assert list(ok) == [True, False]
+    # G2: a twist point outside the r-torsion subgroup passes without the subgroup check only
+    x = (5, 1)
+    while True:
+        y = ser.fp2_sqrt(bn.f2_add(bn.f2_mul(bn.f2_sqr(x), x), bn.B2))
+        if y is not None:
+            break
+        x = (x[0] + 1, x[1])
+    enc = ser.g2_bytes((x, y))
+    _, ok = ctx.decode_points(enc + ser.g2_bytes(bn.G2_GEN), group=2, subgroup_check=True)
+    assert list(ok) == [False, True]
+    pts, ok = ctx.decode_points(enc, group=2, subgroup_check=False)
+    assert ok[0] and np.array_equal(pts[0], bn.g2_to_array([(x, y)])[0])
+
+
+@pytest.mark.parametrize("with_commitment", [False, True])
+@pytest.mark.parametrize("raw", [False, True])
+def test_proof_wire_format_round_trip(ctx, raw, with_commitment):
+    rng = random.Random(47)
+    ar, krs, com, pok = (bn.g1_mul(bn.G1_GEN, rng.randrange(1, R)) for _ in range(4))
+    bs = bn.g2_mul(bn.G2_GEN, rng.randrange(1, R))
+    coms = [com] if with_commitment else []
+    pk = pok if with_commitment else None
+    proof = g16.Proof(bn.g1_to_array([ar])[0], bn.g1_to_array([krs])[0], bn.g2_to_array([bs])[0],
+                      [bn.g1_to_array([c])[0] for c in coms], bn.g1_to_array([pk])[0])
+    data = g16.proof_write_to(ctx, proof, raw=raw)
+    assert data == ser.proof_write(ar, bs, krs, coms, pk, raw=raw)               # byte-exact with the oracle
+    back = g16.proof_read_from(ctx, data, raw=raw)
+    assert np.array_equal(back.Ar, proof.Ar) and np.array_equal(back.Bs, proof.Bs) and np.array_equal(back.Krs, proof.Krs)
+    assert len(back.Commitments) == len(coms) and np.array_equal(back.CommitmentPok, proof.CommitmentPok)
+    with pytest.raises(ValueError):
+        g16.proof_read_from(ctx, data[:-1], raw=raw)
+    tampered = bytearray(data)
+    tampered[5] ^= 0x55
+    try:                                                                          # either rejected or a different point
+        other = g16.proof_read_from(ctx, bytes(tampered), raw=raw)
+        assert not np.array_equal(other.Ar, proof.Ar)
+    except ValueError:
+        pass
+
+
+def test_decode_large_batch_matches_encode(ctx):
+    """2^16 compressed G1 points: decode(encode(P)) == P (the key-loading path)."""
+    rs = np.random.Generator(np.random.PCG64(5))
+    ks = rs.integers(0, 1 << 62, size=(1 << 16, 4), dtype=np.uint64)
+    ks[:, 3] &= np.uint64((1 << 60) - 1)
+    pts = ctx.fixed_base_mul(bn.g1_to_array([bn.G1_GEN])[0], ks, group=1)
+    enc = ctx.encode_points(pts, group=1)
+    dec, ok = ctx.decode_points(enc, group=1)
+    assert ok.all() and np.array_equal(dec, pts)

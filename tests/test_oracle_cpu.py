@@ -232,3 +232,42 @@ def test_cport_keccak(rng):
                                np.stack([np.frombuffer(b"".join(o[1]), np.uint8).reshape(height - 1, 32) for o in opened]),
                                np.array(idxs, np.uint64))
     assert all(bytes(r) == lv[-1][0] for r in roots)
+
+
+# ---- gnark wire formats (oracle/serialize.py): algebraic pins (no vectors exist in the reference)
+def test_point_encodings_round_trip_and_sign_rule():
+    import random
+    from oracle import serialize as ser
+    rng = random.Random(31)
+    # G1 generator (1, 2): y = 2 is the smaller root -> flag 0b10, x big-endian
+    assert ser.g1_bytes(bn.G1_GEN) == bytes([0x80]) + bytes(30) + bytes([1])
+    assert ser.g1_bytes(bn.g1_neg(bn.G1_GEN)) == bytes([0xC0]) + bytes(30) + bytes([1])
+    assert ser.g1_bytes(None) == bytes([0x40]) + bytes(31) and ser.g1_set_bytes(ser.g1_bytes(None)) == (None, 32)
+    for _ in range(8):
+        p1 = bn.g1_mul(bn.G1_GEN, rng.randrange(1, bn.R))
+        p2 = bn.g2_mul(bn.G2_GEN, rng.randrange(1, bn.R))
+        for pt in (p1, bn.g1_neg(p1)):
+            assert ser.g1_set_bytes(ser.g1_bytes(pt)) == (pt, 32)
+            assert ser.g1_set_bytes(ser.g1_raw_bytes(pt)) == (pt, 64)
+        for pt in (p2, bn.g2_neg(p2)):
+            assert ser.g2_set_bytes(ser.g2_bytes(pt)) == (pt, 64)
+            assert ser.g2_set_bytes(ser.g2_raw_bytes(pt)) == (pt, 128)
+        # exactly one of (P, -P) carries the "largest" flag
+        assert (ser.g1_bytes(p1)[0] & 0xC0) != (ser.g1_bytes(bn.g1_neg(p1))[0] & 0xC0)
+        assert (ser.g2_bytes(p2)[0] & 0xC0) != (ser.g2_bytes(bn.g2_neg(p2))[0] & 0xC0)
+    # Fp2 square root: every square has a root, and it squares back
+    for _ in range(8):
+        a = (rng.randrange(bn.P), rng.randrange(bn.P))
+        sq = bn.f2_sqr(a)
+        r = ser.fp2_sqrt(sq)
+        assert r is not None and bn.f2_sqr(r) == sq
+    # invalid encodings are rejected
+    with pytest.raises(ValueError):
+        ser.g1_set_bytes(bytes([0x80]) + bytes(30) + bytes([4]))       # x = 4: x^3 + 3 = 67 is not a square mod p
+    with pytest.raises(ValueError):
+        ser.g1_set_bytes(bytes([0xBF]) + bytes([0xFF] * 31))             # x >= p
+    proof = ser.proof_write(p1, p2, bn.g1_neg(p1), [p1], None)
+    assert len(proof) == 32 + 64 + 32 + 4 + 32 + 32
+    assert ser.proof_read(proof) == (p1, p2, bn.g1_neg(p1), [p1], None, len(proof))
+    raw = ser.proof_write(p1, p2, bn.g1_neg(p1), [], p1, raw=True)
+    assert ser.proof_read(raw) == (p1, p2, bn.g1_neg(p1), [], p1, 64 + 128 + 64 + 4 + 64)

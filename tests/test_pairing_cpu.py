@@ -65,6 +65,11 @@ def test_fp12_tower_matches_oracle(H):
         assert bn.f12_mul(_unflat(out), a) == bn.F12_ONE
         H.host_f12_frob2(_ptr(_flat(a)), _ptr(out))
         assert _unflat(out) == bn.f12_pow(a, P * P)
+        H.host_f12_sqr(_ptr(_flat(a)), _ptr(out))
+        assert _unflat(out) == bn.f12_mul(a, a)
+        for k in (1, 2, 3):
+            H.host_f12_frob(_ptr(_flat(a)), k, _ptr(out))
+            assert _unflat(out) == bn.f12_pow(a, P ** k)
 
 
 def test_pairing_value_and_cofactor(H):
