@@ -83,3 +83,18 @@ def test_merkle_paths_prefix_decoded(ctx):
     Lv = np.stack([np.frombuffer(leaves[i], dtype=np.uint8) for i in idxs])
     roots, okf = ctx.keccak_merkle_paths(Lv, S, A, np.array(idxs, dtype=np.uint64), expected_root=levels[-1][0])
     assert okf.all()
+
+
+def test_external_known_answer_keccak256(ctx):
+    """Ethereum's Keccak-256 of "" and "abc" (public vectors) through k_keccak_f_batch: one padded
+    rate block XORed into the zero state, one permutation, first 32 bytes."""
+    exp = {b"": "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470",
+           b"abc": "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"}
+    states = np.zeros((len(exp), 200), dtype=np.uint8)
+    for k, msg in enumerate(exp):
+        states[k, :len(msg)] = np.frombuffer(msg, dtype=np.uint8)
+        states[k, len(msg)] ^= 0x01
+        states[k, 135] ^= 0x80
+    out = ctx.keccak_f_batch(states.view(np.uint64)).view(np.uint8).reshape(len(exp), 200)
+    for k, msg in enumerate(exp):
+        assert bytes(out[k, :32]).hex() == exp[msg]

@@ -214,3 +214,18 @@ def test_msm_g1_full_size_host_scalars_pipelined(ctx, table):
     bases.free()
     assert np.array_equal(out, cport.g1_gen_mul(cport.fr_dot(ks, sc)))
     assert np.array_equal(out, single)
+
+
+def test_external_known_answer_eip196_double_generator(ctx):
+    """EIP-196 (alt_bn128) test vector 2 * (1, 2), through the fixed-base kernel, the MSM and the
+    host adder — an answer that does not come from this repository's oracle."""
+    exp = bn.g1_to_array([(1368015179489954701390400359078579693043519447331113978918064868415326638035,
+                           9918110051302171585080402603319702774565515993150576347155970296011118125764)])[0]
+    gen = bn.g1_to_array([bn.G1_GEN])[0]
+    assert np.array_equal(ctx.fixed_base_mul(gen, bn.fr_to_mont_array([2]), group=1)[0], exp)
+    bases = ctx.upload_g1(np.stack([gen, gen]))
+    assert np.array_equal(ctx.msm(bases, bn.fr_to_mont_array([1, 1])), exp)
+    assert np.array_equal(ctx.msm(bases, bn.fr_to_mont_array([2, 0])), exp)
+    bases.free()
+    from gnark_whir_b200 import lib
+    assert np.array_equal(lib.g1_add(gen, gen), exp)

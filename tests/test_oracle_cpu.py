@@ -271,3 +271,25 @@ def test_point_encodings_round_trip_and_sign_rule():
     assert ser.proof_read(proof) == (p1, p2, bn.g1_neg(p1), [p1], None, len(proof))
     raw = ser.proof_write(p1, p2, bn.g1_neg(p1), [], p1, raw=True)
     assert ser.proof_read(raw) == (p1, p2, bn.g1_neg(p1), [], p1, 64 + 128 + 64 + 4 + 64)
+
+
+# ---- externally published known answers (not derived from this repo's code)
+def test_external_known_answers():
+    """Vectors from outside this repository, recalled from their public sources:
+    * EIP-196 (alt_bn128 = BN254) ecadd/ecmul test vector: 2 * (1, 2);
+    * gnark-crypto ecc/bn254/fr/element.go and fp/element.go: `one` (= R mod modulus, R = 2^256, i.e. the
+      Montgomery convention every array crossing the C-ABI uses) and qInvNeg (SURVEY §8, reference go.mod:7);
+    * Ethereum's Keccak-256 (legacy 0x01 padding) of "" and "abc" — the permutation under the reference's
+      keccakSponge, through a padding hashlib does not offer."""
+    assert bn.g1_add(bn.G1_GEN, bn.G1_GEN) == (
+        1368015179489954701390400359078579693043519447331113978918064868415326638035,
+        9918110051302171585080402603319702774565515993150576347155970296011118125764)
+    assert bn.g1_mul(bn.G1_GEN, 2) == bn.g1_add(bn.G1_GEN, bn.G1_GEN)
+    fr_one = [12436184717236109307, 3962172157175319849, 7381016538464732718, 1011752739694698287]
+    fp_one = [0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f]
+    assert list(bn.fr_to_mont_array([1])[0]) == fr_one
+    assert list(bn.fp_to_mont_limbs(1)) == fp_one
+    assert (-pow(bn.R, -1, 1 << 64)) % (1 << 64) == 0xc2e1f593efffffff
+    assert (-pow(bn.P, -1, 1 << 64)) % (1 << 64) == 0x87d20782e4866389
+    assert ok.sha3_like(b"", 136, 0x01, 32).hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert ok.sha3_like(b"abc", 136, 0x01, 32).hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
