@@ -240,8 +240,13 @@ def run_b200(args, rank, local_rank, world):
     # integer roofline of the dominant kernel: mixed adds = W digits per point, 10 products of 136 MADs each
     mads = float(win_W) * m * MODMUL_PER_MADD * MAD_PER_MODMUL
     ach = mads / (acc_ms * 1e-3) / 1e12
+    traffic = args.ncu_traffic
+    if traffic is None and args.logn == 24 and args.table and world == 1:
+        traffic = 15.78e9        # profiles/r01c_ncu_k_accumulate_2p24_traffic.txt (ncu, this exact command)
     roofline = {"bound": "integer", "kernel": "k_accumulate<Fp>", "achieved": round(ach, 3), "peak": round(tmad_peak, 3),
-                "unit": "TMAD/s", "frac": round(ach / tmad_peak, 4), "traffic": args.ncu_traffic,
+                "unit": "TMAD/s", "frac": round(ach / tmad_peak, 4), "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum); "
+                                "algorithmic gather bytes per launch = adds_per_point * points * 68",
                 "peak_source": "b200g16_modmul_probe measured in this run (burst; 136 IMAD.WIDE-class multiply-adds per "
                                "Montgomery product); MEASURED_PEAKS.json has no integer-pipe figure",
                 "algorithmic_mads_per_launch": int(mads), "window_bits": win_c, "adds_per_point": win_W,
