@@ -371,7 +371,35 @@ def extras_single_gpu(ctx, st, args):
     ctx.pk_free(pk)
     for v in vecs + [b2]:
         v.free()
+    if not args.no_cpu_baseline:
+        ex["cpu_port_same_box"] = cpu_extras()
     return ex
+
+
+def cpu_extras():
+    """The C port of the other kernels of the metric on this box's host cores (bounded samples; the
+    checker, timed only as the reported CPU baseline)."""
+    from oracle import cport
+    rs = np.random.Generator(np.random.PCG64(SEED + 99))
+    out = {"threads": cport.threads(), "kind": "port (oracle/c/oracle.c, OpenMP), not gnark"}
+
+    def best_of(fn, reps=2):
+        fn()
+        return min(_timed(fn) for _ in range(reps))
+
+    def _timed(fn):
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e3
+    a = rand_fr(rs, 1 << 20)
+    out["ntt_2^20_ms"] = round(best_of(lambda: cport.ntt(a)), 2)
+    a, b, c = rand_fr(rs, 1 << 18), rand_fr(rs, 1 << 18), rand_fr(rs, 1 << 18)
+    out["compute_h_2^18_ms"] = round(best_of(lambda: cport.compute_h(a, b, c, 18)), 2)
+    st = rs.integers(0, 1 << 63, size=(1 << 18, 25), dtype=np.uint64)
+    ms = best_of(lambda: cport.keccak_f_batch(st))
+    out["keccak_f_2^18_states_ms"] = round(ms, 2)
+    out["keccak_Mperm_s"] = round((1 << 18) / ms / 1e3, 2)
+    return out
 
 
 def run_prove_workload(args, rank, local_rank, world):
