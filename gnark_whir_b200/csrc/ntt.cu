@@ -322,9 +322,10 @@ static int ntt_device_impl(b200g16_ctx* ctx, Fr* d_data, Fr* const* vecs, int L,
     A.post = post;
     A.post_bitrev = post_bitrev;
     // tile = 2^k rows x 2^logc columns (8 columns = 256 B chunks unless the vector is tiny)
-    // large transforms: 4 columns (32 KB tiles, 4 CTAs/SM) overlap the load / store phases of one CTA with
-    // the butterflies of the others better than 8 columns (measured: 2^24 3.98 -> 3.85 ms, 2^20 0.251 -> 0.263)
-    const int logc_pref = L >= 23 ? NTT_LOGC - 1 : NTT_LOGC;
+    // 8-level passes of large transforms: 4 columns (32 KB tiles, 4 CTAs/SM) overlap the load / store phases
+    // of one CTA with the butterflies of the others better than 8 columns (64 KB, 3 CTAs/SM); measured:
+    // 2^24 3.98 -> 3.85 ms.  Shorter passes (2^20: 7+7+6, 2^26: 7+7+6+6 levels) keep 8 columns.
+    const int logc_pref = (A.k == NTT_MAX_K && L >= 22) ? NTT_LOGC - 1 : NTT_LOGC;
     int logc = L - A.k < logc_pref ? L - A.k : logc_pref;
     A.logc = logc;
     size_t tiles = n >> (A.k + logc);

@@ -13,7 +13,7 @@ def t_ms(fn, reps=5):
         torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
-for L in (20, 22, 24):
+for L in (16, 18, 20, 22, 23, 24, 25, 26):
     a, b, c = rnd(1 << L), rnd(1 << L), rnd(1 << L)
     ctx.ntt_dev(a.data_ptr(), L, coset=True, decimation=lib.DIF)
     f = t_ms(lambda: ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF))
