@@ -8,9 +8,9 @@
 //
 // Device timeline (one stream): H2D(wires,a,b,c) -> gather wire values into the A / B / K
 // scalar vectors (gnark's filter by pk.InfinityA / pk.InfinityB and by public+committed wires)
-// -> computeH -> MSM B2, Z (scalars = h, straight from computeH's device buffer), A, B1, K enqueued
-// back to back (each MSM's bucket reduction runs on a second stream under the next MSM's
-// accumulation; r*delta, s*delta, -rs*delta, s*delta2 are computed on the host meanwhile)
+// -> MSM B2, A, B1, K -> computeH (a, b, c arrive on the copy stream meanwhile) -> MSM Z (scalars = h,
+// straight from computeH's device buffer), enqueued back to back (each MSM's bucket reduction runs on
+// a second stream under its successor; r*delta, s*delta, -rs*delta, s*delta2 are computed on the host meanwhile)
 // -> one synchronisation -> host: Horner per MSM, then
 //   Ar  = A + alpha + r*delta
 //   Bs1 = B1 + beta + s*delta           Bs = B2 + beta2 + s*delta2
@@ -193,8 +193,10 @@ static void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, co
 
 // d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
 // d_b == nullptr: d_a already holds h (computeH was done elsewhere, e.g. spread over several GPUs).
+// abc_ready: event after which d_a, d_b, d_c are valid (the host path uploads them on the copy stream while
+// the four MSMs that only need the witness already run), or nullptr.
 static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, Fr* d_a, Fr* d_b, Fr* d_c,
-                        const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io) {
+                        const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io, cudaEvent_t abc_ready = nullptr) {
   cudaStream_t st = ctx->stream;
   int ev = *ev_io;
   auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
@@ -211,15 +213,10 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
       ctx->launches++;
     }
   mark();
-  if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
-  mark();
   MsmCfg cfg[5];
   const Fr* scal[5] = {sv[0], sv[1], sv[2], d_a + pk->off_z, sv[1]};
   const size_t cnt[5] = {pk->n_idx[0], pk->n_idx[1], pk->n_idx[2], pk->n_z, pk->n_idx[1]};
-  // G2 first: its bucket reduction is the longest tail and hides behind the four G1 MSMs that follow
-  const int order[5] = {4, 3, 0, 1, 2};
-  for (int k = 0; k < 5; k++) {
-    const int i = order[k];
+  auto enqueue = [&](int i) -> int {
     MsmTable tab;
     const MsmTable* tp = nullptr;
     if (i < 4) {
@@ -230,7 +227,15 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
       B200_TRY(msm_enqueue<Fp2>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
     }
     mark();
-  }
+    return 0;
+  };
+  // The four MSMs over witness values first — G2 leading: its bucket reduction is the longest tail and
+  // hides behind the G1 MSMs that follow — then computeH (a, b, c may still be arriving), then Z over h.
+  for (int i : {4, 0, 1, 2}) B200_TRY(enqueue(i));
+  if (abc_ready) B200_CUDA(cudaStreamWaitEvent(st, abc_ready, 0));
+  if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
+  mark();
+  B200_TRY(enqueue(3));
   B200_TRY(msm_join(ctx));
   DeltaMultiples dm;
   if (!pk->partial) dm = delta_multiples(pk, r, s);  // host work hidden behind the GPU's
@@ -282,20 +287,25 @@ int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires,
   cudaEventRecord(ctx->ev[ev++], st);
   B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
   B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  // a, b, c cross PCIe on the copy stream while the witness MSMs already run (prove_device waits on ev_copy[0])
   DevBuf* bufs[3] = {&ctx->ntt.a, &ctx->ntt.b, &ctx->ntt.c};
   const uint64_t* src[3] = {a, b, c};
+  cudaStream_t cs = ctx->copy_stream;
+  B200_CUDA(cudaEventRecord(ctx->ev_copy[1], st));       // the witness goes first: it gates the MSMs
+  B200_CUDA(cudaStreamWaitEvent(cs, ctx->ev_copy[1], 0));
   for (int i = 0; i < 3; i++) {
     B200_TRY(bufs[i]->ensure(N * sizeof(Fr)));
-    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, cs));
     if (N > n_constraints)
-      B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), st));
+      B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), cs));
   }
+  B200_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
   cudaEventRecord(ctx->ev[ev++], st);
   Fr fr_r, fr_s;
   memcpy(&fr_r, r, 32);
   memcpy(&fr_s, s, 32);
   B200_TRY(prove_device(ctx, pk, ctx->io_a.as<Fr>(), ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(),
-                        fr_r, fr_s, proof_out, &ev));
+                        fr_r, fr_s, proof_out, &ev, ctx->ev_copy[0]));
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   if (h_out) B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));

@@ -229,3 +229,30 @@ def test_external_known_answer_eip196_double_generator(ctx):
     bases.free()
     from gnark_whir_b200 import lib
     assert np.array_equal(lib.g1_add(gen, gen), exp)
+
+
+def test_concurrent_calls_on_one_context(ctx, rng):
+    """gnark calls MultiExp from several goroutines at once (SURVEY §8b threading): calls on one ctx from
+    several OS threads must serialise inside the library and each return its own result."""
+    import threading
+    n = 2000
+    ks, pts = _rand_points(rng, 64)
+    pts = (pts * (n // 64 + 1))[:n]
+    bases = ctx.upload_g1(bn.g1_to_array(pts))
+    scalars = [[rng.randrange(R) for _ in range(n)] for _ in range(6)]
+    arrs = [bn.fr_to_mont_array(s) for s in scalars]
+    expect = [ctx.msm(bases, a) for a in arrs]
+    got = [None] * len(arrs)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = ctx.msm(bases, arrs[i])
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(arrs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    bases.free()
+    for g, e in zip(got, expect):
+        assert np.array_equal(g, e)
+    assert len({e.tobytes() for e in expect}) == len(expect)
