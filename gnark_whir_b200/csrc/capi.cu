@@ -196,7 +196,7 @@ using namespace b200;
 
 extern "C" {
 
-int b200g16_version(void) { return 100; }
+int b200g16_version(void) { return 120; }  // 1.2: window tables, verify / pairing, wire formats, staged computeH
 
 const char* b200g16_last_error(void) { return last_error_buf(); }
 

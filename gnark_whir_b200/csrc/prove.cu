@@ -6,7 +6,7 @@
 // gnark computes inside and right after Solve, go through b200g16_msm_g1 on resident
 // pedersen bases (they are ordinary G1 MSMs).
 //
-// Device timeline (one stream): H2D(wires,a,b,c) -> gather wire values into the A / B / K
+// Device timeline (main stream; copies of a,b,c on the copy stream): H2D(wires) -> gather wire values into the A / B / K
 // scalar vectors (gnark's filter by pk.InfinityA / pk.InfinityB and by public+committed wires)
 // -> MSM B2, A, B1, K -> computeH (a, b, c arrive on the copy stream meanwhile) -> MSM Z (scalars = h,
 // straight from computeH's device buffer), enqueued back to back (each MSM's bucket reduction runs on
