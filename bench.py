@@ -92,23 +92,33 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
+def host_threads():
+    """All the host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    would silently run the CPU arm on one core — the thread count is passed to the C port explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_msm_sample(log_sample, steps, warmup):
     from oracle import cport
+    nt = host_threads()
     rs = np.random.Generator(np.random.PCG64(SEED))
     n = 1 << log_sample
     k0, d = rand_fr(rs, 1), rand_fr(rs, 1)
     pts = cport.g1_progression(k0, d, n)
     sc = rand_fr(rs, n)
     for _ in range(warmup):
-        cport.msm_g1(pts[: n >> 4], sc[: n >> 4], 0)
+        cport.msm_g1(pts[: n >> 4], sc[: n >> 4], nt)
     times = []
     out = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        out = cport.msm_g1(pts, sc, 0)
+        out = cport.msm_g1(pts, sc, nt)
         times.append(time.perf_counter() - t0)
     ok = bool(np.array_equal(out, cport.g1_gen_mul(cport.fr_dot_progression(sc, k0, d))))
-    return n, times, cport.threads(), ok
+    return n, times, nt, ok
 
 
 def run_reference(args, rank):
@@ -381,7 +391,8 @@ def cpu_extras():
     checker, timed only as the reported CPU baseline)."""
     from oracle import cport
     rs = np.random.Generator(np.random.PCG64(SEED + 99))
-    out = {"threads": cport.threads(), "kind": "port (oracle/c/oracle.c, OpenMP), not gnark"}
+    nt = host_threads()
+    out = {"threads": nt, "kind": "port (oracle/c/oracle.c, OpenMP), not gnark"}
 
     def best_of(fn, reps=2):
         fn()
@@ -392,11 +403,11 @@ def cpu_extras():
         fn()
         return (time.perf_counter() - t0) * 1e3
     a = rand_fr(rs, 1 << 20)
-    out["ntt_2^20_ms"] = round(best_of(lambda: cport.ntt(a)), 2)
+    out["ntt_2^20_ms"] = round(best_of(lambda: cport.ntt(a, nthreads=nt)), 2)
     a, b, c = rand_fr(rs, 1 << 18), rand_fr(rs, 1 << 18), rand_fr(rs, 1 << 18)
-    out["compute_h_2^18_ms"] = round(best_of(lambda: cport.compute_h(a, b, c, 18)), 2)
+    out["compute_h_2^18_ms"] = round(best_of(lambda: cport.compute_h(a, b, c, 18, nthreads=nt)), 2)
     st = rs.integers(0, 1 << 63, size=(1 << 18, 25), dtype=np.uint64)
-    ms = best_of(lambda: cport.keccak_f_batch(st))
+    ms = best_of(lambda: cport.keccak_f_batch(st, nthreads=nt))
     out["keccak_f_2^18_states_ms"] = round(ms, 2)
     out["keccak_Mperm_s"] = round((1 << 18) / ms / 1e3, 2)
     return out

@@ -1,0 +1,138 @@
+"""GPU parity at BASELINE.json's full sizes, through size-independent properties (the oracle cannot
+finish these sizes in seconds, except where the C port's closed forms can):
+
+  configs[1]  G1 MSM 2^24: result == [sum s_i k_i] G (dot product by the C oracle, one scalar mul),
+              and linearity MSM(s) + MSM(t) == MSM(s + t) with s + t formed on the host
+  configs[2]  Fr NTT 2^24 / computeH 2^22: forward/inverse round trips in both conventions, linearity,
+              and the defining identity A*B - C == H * (X^N - 1) checked at a random point
+  configs[3]  Keccak: 2^20 Merkle paths, a random sample compared with the C oracle + all roots of paths
+              opened from one real tree equal that tree's root
+"""
+import numpy as np
+import pytest
+import torch
+
+from gnark_whir_b200 import lib
+from oracle import bn254 as bn
+from oracle import cport
+from oracle.bn254 import R
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_fr(rs, n):
+    a = rs.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a
+
+
+def test_msm_g1_2p24_closed_form_and_linearity(ctx):
+    rs = np.random.Generator(np.random.PCG64(2024))
+    n = 1 << 24
+    ks = _rand_fr(rs, n)
+    bases = ctx.fixed_base_mul(bn.g1_to_array([bn.G1_GEN])[0], ks, group=1, resident=True)
+    s, t = _rand_fr(rs, n), _rand_fr(rs, n)
+    ds, dt = torch.from_numpy(s.view(np.int64)).cuda(), torch.from_numpy(t.view(np.int64)).cuda()
+    ms = ctx.msm(bases, ds.data_ptr(), n=n)
+    assert np.array_equal(ms, cport.g1_gen_mul(cport.fr_dot(ks, s)))
+    bases.precompute(0)                                   # the same vector with a window table
+    assert np.array_equal(ctx.msm(bases, ds.data_ptr(), n=n), ms)
+    mt = ctx.msm(bases, dt.data_ptr(), n=n)
+    # s + t as plain 256-bit integers (both < 2^252, so no reduction): Montgomery form is additive
+    carry = np.zeros(n, dtype=np.uint64)
+    st = np.empty_like(s)
+    for j in range(4):
+        a = s[:, j].astype(object) + t[:, j].astype(object) + carry.astype(object)
+        st[:, j] = (a & ((1 << 64) - 1)).astype(np.uint64)
+        carry = (a >> 64).astype(np.uint64)
+    dst = torch.from_numpy(st.view(np.int64)).cuda()
+    assert np.array_equal(ctx.msm(bases, dst.data_ptr(), n=n), lib.g1_add(ms, mt))
+    bases.free()
+
+
+def test_ntt_2p24_round_trips_and_linearity(ctx):
+    L, n = 24, 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def rnd():
+        a = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+        a[:, 3] &= (1 << 60) - 1
+        return a
+    a = rnd()
+    ref = a.clone()
+    ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)
+    assert not torch.equal(a, ref)
+    ctx.ntt_dev(a.data_ptr(), L, inverse=True, decimation=lib.DIT)
+    assert torch.equal(a, ref)
+    ctx.ntt_dev(a.data_ptr(), L, coset=True, decimation=lib.DIT)     # input taken as bit-reversed
+    ctx.ntt_dev(a.data_ptr(), L, inverse=True, coset=True, decimation=lib.DIF)
+    assert torch.equal(a, ref)
+    # linearity: NTT(x) + NTT(y) == NTT(x + y); x + y formed as plain integers (both < 2^252, no reduction)
+    x, y = ref, rnd()
+    xs, ys = x.cpu().numpy().view(np.uint64), y.cpu().numpy().view(np.uint64)
+    carry = np.zeros(n, dtype=np.uint64)
+    out = np.empty_like(xs)
+    for j in range(4):
+        lo = xs[:, j] + ys[:, j]
+        c1 = (lo < xs[:, j]).astype(np.uint64)
+        lo2 = lo + carry
+        c2 = (lo2 < lo).astype(np.uint64)
+        out[:, j] = lo2
+        carry = c1 + c2
+    s = torch.from_numpy(out.view(np.int64)).cuda()
+    for v in (x, y, s):
+        ctx.ntt_dev(v.data_ptr(), L, decimation=lib.DIF)
+    # field addition of the two spectra on the host for a strided sample
+    idx = np.arange(0, n, 4099)
+    X = bn.fr_from_mont_array(x[idx].cpu().numpy().view(np.uint64))
+    Y = bn.fr_from_mont_array(y[idx].cpu().numpy().view(np.uint64))
+    S = bn.fr_from_mont_array(s[idx].cpu().numpy().view(np.uint64))
+    assert all((p + q) % R == r for p, q, r in zip(X, Y, S))
+
+
+def test_compute_h_2p22_satisfies_its_defining_identity(ctx):
+    """h = computeH(a, b, c): with A, B, C the interpolants of a, b, c on the domain,
+    A(z) B(z) - C(z) == H(z) (z^N - 1).  Checked at coset points z = g w^j, where all four evaluations
+    come from separate library transforms (the field identity itself is verified in python big ints);
+    computeH is also pinned against the C oracle at 2^16 in the same test."""
+    rs = np.random.Generator(np.random.PCG64(99))
+    a, b, c = _rand_fr(rs, 1 << 16), _rand_fr(rs, 1 << 16), _rand_fr(rs, 1 << 16)
+    assert np.array_equal(ctx.compute_h(a, b, c, 16), cport.compute_h(a, b, c, 16))
+    L, n = 22, 1 << 22
+    a, b, c = _rand_fr(rs, n), _rand_fr(rs, n), _rand_fr(rs, n)
+    h = ctx.compute_h(a, b, c, L)                                   # bit-reversed coefficient order
+    # coset evaluations: cosetNTT(iNTT(v)) for v in a, b, c; cosetNTT_DIT(h) takes the bit-reversed h
+    ev = []
+    for v in (a, b, c):
+        coef = ctx.ntt(v, inverse=True, decimation=lib.DIF)
+        ev.append(ctx.ntt(coef, coset=True, decimation=lib.DIT))
+    hev = ctx.ntt(h, coset=True, decimation=lib.DIT)
+    den = (pow(5, n, R) - 1) % R                                    # z^N - 1 is constant on the coset
+    idx = np.arange(0, n, 8191)
+    A, B, C_, H = (bn.fr_from_mont_array(x[idx]) for x in (ev[0], ev[1], ev[2], hev))
+    assert all((p * q - r) % R == hh * den % R for p, q, r, hh in zip(A, B, C_, H))
+
+
+def test_keccak_merkle_2p20_paths(ctx):
+    from oracle import keccak as ok
+    rs = np.random.Generator(np.random.PCG64(5))
+    q, height, leaf_len = 1 << 20, 20, 512
+    leaves = rs.integers(0, 256, size=(q, leaf_len), dtype=np.uint8)
+    sib = rs.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    auth = rs.integers(0, 256, size=(q, height - 1, 32), dtype=np.uint8)
+    idx = rs.integers(0, 1 << height, size=q, dtype=np.uint64)
+    roots, _ = ctx.keccak_merkle_paths(leaves, sib, auth, idx)
+    pick = rs.integers(0, q, size=256)
+    exp = cport.merkle_paths(leaves[pick], sib[pick], auth[pick], idx[pick])
+    assert np.array_equal(roots[pick], exp)
+    # a real tree (2^10 leaves): every opened path recomputes the tree's root
+    h2 = 10
+    tl = [bytes(rs.integers(0, 256, size=64, dtype=np.uint8)) for _ in range(1 << h2)]
+    lv = ok.build_merkle_tree(tl)
+    opened = [ok.merkle_open(lv, i) for i in range(1 << h2)]
+    roots, okf = ctx.keccak_merkle_paths(
+        np.stack([np.frombuffer(x, np.uint8) for x in tl]),
+        np.stack([np.frombuffer(o[0], np.uint8) for o in opened]),
+        np.stack([np.frombuffer(b"".join(o[1]), np.uint8).reshape(h2 - 1, 32) for o in opened]),
+        np.arange(1 << h2, dtype=np.uint64), expected_root=lv[-1][0])
+    assert okf.all()
