@@ -376,7 +376,7 @@ def extras_single_gpu(ctx, st, args):
     ex["groth16_prove_synthetic"] = {
         "log2_constraints": Lp, "wires": Np, "witness_mix": "40% 0/1, 30% bytes, 30% uniform (SURVEY §8d config 1)",
         "ms": round(best, 3), "window_tables": bool(args.table),
-        "phases_ms[h2d,gather,msmB2,msmA,msmB1,msmK,computeH,msmZ]": [round(x, 3) for x in (ph or [])],
+        "phases_ms[h2d,gather,msmB2,msmB1,msmA,msmK,computeH,msmZ]": [round(x, 3) for x in (ph or [])],
         "note": "inputs resident in HBM; wall-clock around b200g16_prove_dev incl. host finish"}
     ctx.pk_free(pk)
     for v in vecs + [b2]:
@@ -526,7 +526,7 @@ def run_prove_workload(args, rank, local_rank, world):
                                       "; all_gather of 5 partial points"},
             "e2e": e2e,
             "gpu_launches": launches,
-            "phases_ms_rank0[h2d,gather,msmB2,msmA,msmB1,msmK,computeH,msmZ]": [round(x, 3) for x in ph],
+            "phases_ms_rank0[h2d,gather,msmB2,msmB1,msmA,msmK,computeH,msmZ]": [round(x, 3) for x in ph],
             "proof_krs_limb0": int(res["krs"][0])}))
     ctx.pk_free(pk)
     for v in list(vec.values()) + [b2]:

@@ -4,11 +4,11 @@
 
 namespace b200 {
 // instantiated in msm_g1.cu / msm_g2.cu
-extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
 extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
 extern template int msm_device<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, Affine<Fp>*);
 extern template int msm_build_table<Fp>(b200g16_ctx*, Affine<Fp>*, size_t, int, int);
-extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
 extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
 extern template int msm_device<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, Affine<Fp2>*);
 extern template int msm_build_table<Fp2>(b200g16_ctx*, Affine<Fp2>*, size_t, int, int);
@@ -226,7 +226,7 @@ int b200g16_init(int device, b200g16_ctx** out) {
   B200_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev_copy) B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : ctx->ev) B200_CUDA(cudaEventCreate(&ev));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < MSM_SETS; i++) {
     B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_front[i], cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming));
   }
@@ -239,15 +239,16 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->tail_stream);
-  DevBuf* bufs[] = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->msm.counts[0], &ctx->msm.counts[1],
-                    &ctx->msm.partials[0], &ctx->msm.partials[1], &ctx->msm.chunks[0], &ctx->msm.chunks[1],
-                    &ctx->msm.misc[0], &ctx->msm.misc[1], &ctx->msm.tasks[0], &ctx->msm.tasks[1],
-                    &ctx->ntt.a,       &ctx->ntt.b,       &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->io_a,
-                    &ctx->io_b,        &ctx->io_c};
+  std::vector<DevBuf*> bufs = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->ntt.a, &ctx->ntt.b,
+                               &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->io_a,  &ctx->io_b,
+                               &ctx->io_c};
+  for (int i = 0; i < MSM_SETS; i++)
+    for (DevBuf* b : {&ctx->msm.counts[i], &ctx->msm.partials[i], &ctx->msm.chunks[i], &ctx->msm.misc[i], &ctx->msm.tasks[i]})
+      bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
   if (ctx->msm.pinned) cudaFreeHost(ctx->msm.pinned);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
+  for (int i = 0; i < MSM_SETS; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
   for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->tail_stream);

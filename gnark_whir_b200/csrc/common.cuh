@@ -64,10 +64,12 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int MSM_SETS = 3;  // rotating buffer sets: an MSM only waits for the tail of the MSM three calls back
+
 struct MsmWorkspace {
-  // everything the "tail" of an MSM reads (merge of split buckets + bucket reduction) exists twice: the
-  // tail runs on a second stream while the next MSM's sort + accumulate ("front") fills the other set
-  DevBuf scalars, digits, entries, counts[2], partials[2], chunks[2], misc[2], tasks[2];
+  // everything the "tail" of an MSM reads (merge of split buckets + bucket reduction) exists MSM_SETS times: the
+  // tail runs on a second stream while the next MSMs' sort + accumulate ("front") fill the other sets
+  DevBuf scalars, digits, entries, counts[MSM_SETS], partials[MSM_SETS], chunks[MSM_SETS], misc[MSM_SETS], tasks[MSM_SETS];
   void* pinned = nullptr;  // small host staging for window sums
   size_t pinned_cap = 0;
 };
@@ -85,6 +87,18 @@ struct MsmTable {
   uint32_t off;     // first point of the sub-range this MSM uses
 };
 
+// The sorted state (digits, entries, counts, offsets, tasks) the last MSM left behind.  A following MSM over
+// the SAME scalar vector and the same decomposition — groth16's Bs1 (G1) right after Bs2 (G2), both over
+// wireValuesB — skips its sort phase and accumulates over these lists with its own bases.
+struct MsmSorted {
+  const void* scalars = nullptr;
+  size_t n = 0;
+  int c = 0;
+  uint32_t bstride = 0, ent_stride = 0, ent_off = 0;
+  int par = 0;
+  bool valid = false;
+};
+
 struct Timings {
   // last-call device timings in ms (CUDA events on ctx stream); index = phase
   float ms[16];
@@ -100,9 +114,11 @@ struct b200g16_ctx {
   cudaStream_t tail_stream = nullptr;   // bucket reductions (latency-bound, few threads) overlap the next MSM
   cudaStream_t copy_stream = nullptr;   // H2D of host scalars, pipelined against the MSM of the previous piece
   cudaEvent_t ev_copy[4] = {};
-  cudaEvent_t ev_front[2] = {}, ev_tail[2] = {};
-  bool tail_pending[2] = {false, false};
+  cudaEvent_t ev_front[b200::MSM_SETS] = {}, ev_tail[b200::MSM_SETS] = {};
+  bool tail_pending[b200::MSM_SETS] = {};
   int msm_parity = 0;
+  b200::MsmSorted last_sort;
+  int sort_reader[b200::MSM_SETS] = {-1, -1, -1};  // sort_reader[p] = set of an MSM whose tail still reads sorted set p (shared)
   cudaEvent_t ev[18] = {};
   std::mutex mu;  // one call at a time per ctx (gnark calls MSMs from several goroutines)
   b200::MsmWorkspace msm;

@@ -186,9 +186,11 @@ constexpr int MSM_MAX_WINDOWS = 130;
 
 // Enqueue one MSM on ctx->stream; its W window sums land in pinned slot `slot` once the stream
 // drains.  No host synchronisation.  record_events: fill ctx->ev for b200g16_last_timings.
+// share_sort: the caller guarantees that d_scalars still holds what the previous enqueue saw under the
+// same pointer; if that MSM used the same decomposition its sorted lists are reused (no sort phase).
 template <class F>
 int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab, const Fr* d_scalars, size_t n, int slot,
-                MsmCfg* cfg_out, bool record_events) {
+                MsmCfg* cfg_out, bool record_events, bool share_sort = false) {
   MsmCfg cfg;
   memset(&cfg, 0, sizeof(cfg));
   *cfg_out = cfg;
@@ -218,15 +220,20 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   size_t max_tasks = (size_t)cfg.nb + cfg.target_tasks + 64;
 
   MsmWorkspace& ws = ctx->msm;
-  const int par = ctx->msm_parity;
-  ctx->msm_parity ^= 1;
+  const int par = ctx->msm_parity;  // own set: partials, chunks
+  ctx->msm_parity = (par + 1) % MSM_SETS;
+  const MsmSorted& ls = ctx->last_sort;
+  const bool reuse = share_sort && ls.valid && ls.par != par && ls.scalars == (const void*)d_scalars && ls.n == n &&
+                     ls.c == cfg.c && ls.bstride == cfg.bstride && ls.ent_stride == cfg.ent_stride &&
+                     ls.ent_off == cfg.ent_off;
+  const int spar = reuse ? ls.par : par;  // set holding the sorted state: counts, offsets, tasks, totals
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
   B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
-  B200_TRY(ws.counts[par].ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
+  B200_TRY(ws.counts[spar].ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
   // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
   const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
-  B200_TRY(ws.misc[par].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
-  B200_TRY(ws.tasks[par].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
+  B200_TRY(ws.misc[spar].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
+  B200_TRY(ws.tasks[spar].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
   B200_TRY(ws.partials[par].ensure(max_tasks * sizeof(XYZZ<F>)));
   B200_TRY(ws.chunks[par].ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
@@ -237,14 +244,14 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   }
   if (cfg.W > MSM_MAX_WINDOWS - 2) return fail(B200G16_ERR_ARG, "msm: too many windows");
 
-  uint32_t* counts = ws.counts[par].as<uint32_t>();
+  uint32_t* counts = ws.counts[spar].as<uint32_t>();
   uint32_t* offsets = counts + cfg.nb;
   uint32_t* cursor = offsets + cfg.nb;
   uint32_t* task_off = cursor + cfg.nb;
-  uint32_t* totals = ws.misc[par].as<uint32_t>();
+  uint32_t* totals = ws.misc[spar].as<uint32_t>();
   int32_t* digits = ws.digits.as<int32_t>();
   uint32_t* entries = ws.entries.as<uint32_t>();
-  uint32_t* task_bucket = ws.tasks[par].as<uint32_t>();
+  uint32_t* task_bucket = ws.tasks[spar].as<uint32_t>();
   uint32_t* task_order = task_bucket + max_tasks;
   XYZZ<F>* partials = ws.partials[par].as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks[par].as<XYZZ<F>>();
@@ -255,11 +262,29 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   auto mark = [&]() { if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
   // buffer set `par` may still be read by the tail of the MSM before last
   if (ctx->tail_pending[par]) B200_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[par], 0));
-
-  B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
-                          task_bucket, task_order, (uint32_t)max_tasks,
-                          reinterpret_cast<uint32_t*>(ws.misc[par].as<char>() + scan_off),
-                          record_events ? &ev : nullptr));
+  if (!reuse) {
+    // ... and its sorted state by the tail of an MSM that shared it
+    const int rd = ctx->sort_reader[par];
+    if (rd >= 0 && ctx->tail_pending[rd]) B200_CUDA(cudaStreamWaitEvent(st, ctx->ev_tail[rd], 0));
+    ctx->sort_reader[par] = -1;
+    ctx->last_sort.valid = false;
+    B200_TRY(msm_sort_phase(ctx, cfg, d_scalars, n32, digits, counts, offsets, cursor, task_off, totals, entries,
+                            task_bucket, task_order, (uint32_t)max_tasks,
+                            reinterpret_cast<uint32_t*>(ws.misc[par].as<char>() + scan_off),
+                            record_events ? &ev : nullptr));
+    ctx->last_sort.scalars = d_scalars;
+    ctx->last_sort.n = n;
+    ctx->last_sort.c = cfg.c;
+    ctx->last_sort.bstride = cfg.bstride;
+    ctx->last_sort.ent_stride = cfg.ent_stride;
+    ctx->last_sort.ent_off = cfg.ent_off;
+    ctx->last_sort.par = par;
+    ctx->last_sort.valid = true;
+  } else {
+    ctx->sort_reader[spar] = par;   // this MSM's tail reads set spar: its next writer must wait for it
+    ctx->last_sort.valid = false;   // one sharer per sort
+    if (record_events) { mark(); mark(); mark(); }
+  }
   k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_order, task_bucket, offsets, counts, task_off,
                                                          totals, partials);
   mark();
@@ -300,7 +325,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
 // Make ctx->stream wait for every outstanding bucket reduction: after this, synchronising ctx->stream
 // guarantees all enqueued MSM results are in their pinned slots.
 inline int msm_join(b200g16_ctx* ctx) {
-  for (int p = 0; p < 2; p++)
+  for (int p = 0; p < MSM_SETS; p++)
     if (ctx->tail_pending[p]) {
       B200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail[p], 0));
       ctx->tail_pending[p] = false;

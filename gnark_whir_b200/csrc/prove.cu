@@ -8,7 +8,7 @@
 //
 // Device timeline (main stream; copies of a,b,c on the copy stream): H2D(wires) -> gather wire values into the A / B / K
 // scalar vectors (gnark's filter by pk.InfinityA / pk.InfinityB and by public+committed wires)
-// -> MSM B2, A, B1, K -> computeH (a, b, c arrive on the copy stream meanwhile) -> MSM Z (scalars = h,
+// -> MSM B2, B1 (on B2's sorted lists: same scalars), A, K -> computeH (a, b, c arrive on the copy stream meanwhile) -> MSM Z (scalars = h,
 // straight from computeH's device buffer), enqueued back to back (each MSM's bucket reduction runs on
 // a second stream under its successor; r*delta, s*delta, -rs*delta, s*delta2 are computed on the host meanwhile)
 // -> one synchronisation -> host: Horner per MSM, then
@@ -20,9 +20,9 @@
 namespace b200 {
 int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
 // instantiated in msm_g1.cu / msm_g2.cu
-extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
 extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
-extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool);
+extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
 extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
 }  // namespace b200
 
@@ -221,7 +221,8 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
     const MsmTable* tp = nullptr;
     if (i < 4) {
       const G1Affine* pts = msm_operand<Fp>(pk->vec[i], 0, &tab, &tp);
-      B200_TRY(msm_enqueue<Fp>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
+      // Bs1 runs over the same scalar vector as Bs2 (wireValuesB): it reuses Bs2's sorted lists
+      B200_TRY(msm_enqueue<Fp>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false, /*share_sort=*/i == 1));
     } else {
       const G2Affine* pts = msm_operand<Fp2>(pk->vec[i], 0, &tab, &tp);
       B200_TRY(msm_enqueue<Fp2>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
@@ -231,7 +232,7 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   };
   // The four MSMs over witness values first — G2 leading: its bucket reduction is the longest tail and
   // hides behind the G1 MSMs that follow — then computeH (a, b, c may still be arriving), then Z over h.
-  for (int i : {4, 0, 1, 2}) B200_TRY(enqueue(i));
+  for (int i : {4, 1, 0, 2}) B200_TRY(enqueue(i));
   if (abc_ready) B200_CUDA(cudaStreamWaitEvent(st, abc_ready, 0));
   if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
   mark();

@@ -248,7 +248,12 @@ int oracle_msm_g1(const u64* points, const u64* scalars, size_t n, int threads, 
       digits[(size_t)w * n + i] = (int32_t)d;
     }
   }
-  int S = threads > W ? (threads + W - 1) / W : 1;       /* point-range splits per window */
+  /* point-range splits per window: gnark's MultiExp splits the points when it has more workers than
+   * windows ("nbSplits"); W windows rarely divide the thread count evenly, so aim for >= 2 tasks per
+   * thread and let the dynamic schedule balance them */
+  int S = (2 * threads + W - 1) / W;
+  if (S < 1) S = 1;
+  if ((size_t)S > n / 1024 + 1) S = (int)(n / 1024 + 1);
   size_t nb = (size_t)1 << (c - 1);
   g1x* sums = (g1x*)calloc((size_t)W * S, sizeof(g1x));
   int fail = 0;
