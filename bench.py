@@ -434,7 +434,14 @@ def run_prove_workload(args, rank, local_rank, world):
     rs = np.random.Generator(np.random.PCG64(SEED + 31 * rank))
     g1, g2 = g16.g1_point(g16.G1_GEN), g16.g2_point(g16.G2_GEN)
     lens = {"a": N, "b": N, "k": N - 1, "z": N - 1}
-    spans = {k: sharded.shard_range(v, rank, world) for k, v in lens.items()}
+    # computeH for N > 1: spread over three ranks (default), the same overlapped with the other ranks' witness
+    # MSMs and with weighted shards (--overlap-h; measured no better: NCCL's kernels do not get SMs under the
+    # saturating accumulate kernel), or replicated (--replicated-h)
+    distributed_h = world > 1 and not args.replicated_h
+    overlap_h = distributed_h and args.overlap_h
+    weights = sharded.prove_weights(world, args.h_share) if overlap_h else [1.0] * world
+    spans = {k: (sharded.shard_range(v, rank, world) if k == "z" else sharded.shard_range_weighted(v, rank, weights))
+             for k, v in lens.items()}
     vec = {k: ctx.fixed_base_mul(g1, rand_fr(rs, hi - lo), group=1, resident=True) for k, (lo, hi) in spans.items()}
     b2 = ctx.fixed_base_mul(g2, rand_fr(rs, spans["b"][1] - spans["b"][0]), group=2, resident=True)
     if args.table:
@@ -466,12 +473,15 @@ def run_prove_workload(args, rank, local_rank, world):
 
     def step():
         aa, bb, cc = a.clone(), b.clone(), c.clone()        # computeH works in place
-        if world == 1 or args.replicated_h:
-            part = ctx.prove_dev(pk, wires.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
-        else:       # a, b, c transformed on three ranks, broadcast, finished everywhere
+        if overlap_h:       # a, b, c transformed on three ranks under the other ranks' witness MSMs, broadcast, finished everywhere
             torch.cuda.synchronize()                        # clones (torch stream) before the library's stream
+            return sharded.prove_distributed(ctx, pk, wires, aa, bb, cc, L, rr, ss, device=dev)
+        if distributed_h:   # a, b, c transformed on three ranks, broadcast, finished everywhere, then the five MSMs
+            torch.cuda.synchronize()
             sharded.compute_h_distributed(ctx, aa, bb, cc, L)
             part = ctx.prove_h_dev(pk, wires.data_ptr(), aa.data_ptr(), rr, ss)
+        else:
+            part = ctx.prove_dev(pk, wires.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
         if world == 1:
             return part
         t = torch.from_numpy(sharded.pack_partials(part).view(np.int64).copy()).to(dev)
@@ -522,7 +532,9 @@ def run_prove_workload(args, rank, local_rank, world):
                        "window_tables": bool(args.table),
                        "parallelism": f"pk point-range shards x{world}; computeH " +
                                       ("replicated" if (world == 1 or args.replicated_h) else
-                                       "spread over 3 ranks (a, b, c) + 3 NCCL broadcasts") +
+                                       "spread over 3 ranks (a, b, c) + 3 NCCL broadcasts" +
+                                       (f", under the other ranks' witness MSMs; witness-MSM shard weights "
+                                        f"{[round(w, 2) for w in weights]}" if overlap_h else "")) +
                                       "; all_gather of 5 partial points"},
             "e2e": e2e,
             "gpu_launches": launches,
@@ -551,6 +563,10 @@ def main():
     ap.add_argument("--prove-logn", type=int, default=20)
     ap.add_argument("--no-table", dest="table", action="store_false",
                     help="run the MSM without the window table over the resident bases (b200g16_bases_precompute)")
+    ap.add_argument("--overlap-h", action="store_true",
+                    help="prove workload, N>1: sharded.prove_distributed (computeH stages overlapped with the witness MSMs)")
+    ap.add_argument("--h-share", type=float, default=None,
+                    help="prove workload, N>=3: relative witness-MSM shard size of the three ranks that also transform a, b, c")
     ap.add_argument("--replicated-h", action="store_true",
                     help="prove workload, N>1: every rank runs the whole computeH instead of spreading it over 3 ranks")
     ap.add_argument("--no-extras", action="store_true")

@@ -87,6 +87,20 @@ struct MsmTable {
   uint32_t off;     // first point of the sub-range this MSM uses
 };
 
+struct MsmCfg {
+  int c;          // window bits
+  int W;          // windows
+  uint32_t nbw;   // buckets per window = 2^(c-1)
+  uint32_t nb;    // buckets in total: W * nbw, or nbw when the bases carry a window table
+  int Wr;         // window sums produced by the reduction: W, or 1 with a window table
+  uint32_t bstride;     // bucket-index stride between windows: nbw, or 0 with a window table
+  uint32_t ent_stride;  // entry = w * ent_stride + ent_off + i  (index into the bases / the table)
+  uint32_t ent_off;
+  uint32_t target_tasks;  // accumulate tasks wanted even for skewed inputs (device picks the task size)
+  uint32_t ch;    // buckets per reduce chunk
+  uint32_t nch;   // chunks per window
+};
+
 // The sorted state (digits, entries, counts, offsets, tasks) the last MSM left behind.  A following MSM over
 // the SAME scalar vector and the same decomposition — groth16's Bs1 (G1) right after Bs2 (G2), both over
 // wireValuesB — skips its sort phase and accumulates over these lists with its own bases.
@@ -118,6 +132,10 @@ struct b200g16_ctx {
   bool tail_pending[b200::MSM_SETS] = {};
   int msm_parity = 0;
   b200::MsmSorted last_sort;
+  // a prove between its two halves (b200g16_prove_begin_dev / _end_dev): decompositions of the five MSMs
+  b200::MsmCfg prove_cfg[5] = {};
+  const struct b200g16_pk* prove_pk = nullptr;
+  bool prove_active = false;
   int sort_reader[b200::MSM_SETS] = {-1, -1, -1};  // sort_reader[p] = set of an MSM whose tail still reads sorted set p (shared)
   cudaEvent_t ev[18] = {};
   std::mutex mu;  // one call at a time per ctx (gnark calls MSMs from several goroutines)

@@ -25,19 +25,7 @@
 
 namespace b200 {
 
-struct MsmCfg {
-  int c;          // window bits
-  int W;          // windows
-  uint32_t nbw;   // buckets per window = 2^(c-1)
-  uint32_t nb;    // buckets in total: W * nbw, or nbw when the bases carry a window table
-  int Wr;         // window sums produced by the reduction: W, or 1 with a window table
-  uint32_t bstride;     // bucket-index stride between windows: nbw, or 0 with a window table
-  uint32_t ent_stride;  // entry = w * ent_stride + ent_off + i  (index into the bases / the table)
-  uint32_t ent_off;
-  uint32_t target_tasks;  // accumulate tasks wanted even for skewed inputs (device picks the task size)
-  uint32_t ch;    // buckets per reduce chunk
-  uint32_t nch;   // chunks per window
-};
+// (struct MsmCfg lives in common.cuh)
 
 // msm_common.cu
 int msm_num_windows(int c);

@@ -191,16 +191,26 @@ static void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, co
   memcpy(out->bs1, &bs1, 64);
 }
 
-// d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
-// d_b == nullptr: d_a already holds h (computeH was done elsewhere, e.g. spread over several GPUs).
-// abc_ready: event after which d_a, d_b, d_c are valid (the host path uploads them on the copy stream while
-// the four MSMs that only need the witness already run), or nullptr.
-static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, Fr* d_a, Fr* d_b, Fr* d_c,
-                        const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io, cudaEvent_t abc_ready = nullptr) {
+// A prove runs in two halves — prove_front: the four MSMs that only need the witness; prove_back: the Z MSM
+// over h, the join and the host assembly — with its state (ctx->prove_cfg, prove_pk) kept on the ctx.
+static int prove_enqueue_one(b200g16_ctx* ctx, const b200g16_pk* pk, int i, const Fr* scalars, size_t count, MsmCfg* cfg) {
+  MsmTable tab;
+  const MsmTable* tp = nullptr;
+  if (i < 4) {
+    const G1Affine* pts = msm_operand<Fp>(pk->vec[i], 0, &tab, &tp);
+    // Bs1 runs over the same scalar vector as Bs2 (wireValuesB): it reuses Bs2's sorted lists
+    return msm_enqueue<Fp>(ctx, pts, tp, scalars, count, i, cfg, false, /*share_sort=*/i == 1);
+  }
+  const G2Affine* pts = msm_operand<Fp2>(pk->vec[i], 0, &tab, &tp);
+  return msm_enqueue<Fp2>(ctx, pts, tp, scalars, count, i, cfg, false);
+}
+
+// Gathers + the four MSMs over witness values — G2 leading: its bucket reduction is the longest tail and
+// hides behind the G1 MSMs that follow.  Enqueues only; no synchronisation.
+static int prove_front(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, int* ev_io) {
   cudaStream_t st = ctx->stream;
   int ev = *ev_io;
   auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };
-  // scalar vectors
   size_t tot = pk->n_idx[0] + pk->n_idx[1] + pk->n_idx[2];
   B200_TRY(ctx->io_b.ensure((tot ? tot : 1) * sizeof(Fr)));
   Fr* sv[3];
@@ -213,35 +223,33 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
       ctx->launches++;
     }
   mark();
-  MsmCfg cfg[5];
-  const Fr* scal[5] = {sv[0], sv[1], sv[2], d_a + pk->off_z, sv[1]};
-  const size_t cnt[5] = {pk->n_idx[0], pk->n_idx[1], pk->n_idx[2], pk->n_z, pk->n_idx[1]};
-  auto enqueue = [&](int i) -> int {
-    MsmTable tab;
-    const MsmTable* tp = nullptr;
-    if (i < 4) {
-      const G1Affine* pts = msm_operand<Fp>(pk->vec[i], 0, &tab, &tp);
-      // Bs1 runs over the same scalar vector as Bs2 (wireValuesB): it reuses Bs2's sorted lists
-      B200_TRY(msm_enqueue<Fp>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false, /*share_sort=*/i == 1));
-    } else {
-      const G2Affine* pts = msm_operand<Fp2>(pk->vec[i], 0, &tab, &tp);
-      B200_TRY(msm_enqueue<Fp2>(ctx, pts, tp, scal[i], cnt[i], i, &cfg[i], false));
-    }
+  const Fr* scal[5] = {sv[0], sv[1], sv[2], nullptr, sv[1]};
+  const size_t cnt[5] = {pk->n_idx[0], pk->n_idx[1], pk->n_idx[2], 0, pk->n_idx[1]};
+  for (int i : {4, 1, 0, 2}) {
+    B200_TRY(prove_enqueue_one(ctx, pk, i, scal[i], cnt[i], &ctx->prove_cfg[i]));
     mark();
-    return 0;
-  };
-  // The four MSMs over witness values first — G2 leading: its bucket reduction is the longest tail and
-  // hides behind the G1 MSMs that follow — then computeH (a, b, c may still be arriving), then Z over h.
-  for (int i : {4, 1, 0, 2}) B200_TRY(enqueue(i));
-  if (abc_ready) B200_CUDA(cudaStreamWaitEvent(st, abc_ready, 0));
-  if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
-  mark();
-  B200_TRY(enqueue(3));
+  }
+  ctx->prove_pk = pk;
+  ctx->prove_active = true;
+  *ev_io = ev;
+  return 0;
+}
+
+// d_h: h (N elements, bit-reversed).  Z MSM, join, host assembly.
+static int prove_back(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_h, const Fr& r, const Fr& s,
+                      b200g16_proof* out, int* ev_io) {
+  if (!ctx->prove_active || ctx->prove_pk != pk) return fail(B200G16_ERR_STATE, "prove: no matching prove_begin on this ctx");
+  ctx->prove_active = false;
+  cudaStream_t st = ctx->stream;
+  int ev = *ev_io;
+  B200_TRY(prove_enqueue_one(ctx, pk, 3, d_h + pk->off_z, pk->n_z, &ctx->prove_cfg[3]));
+  if (ev < 18) cudaEventRecord(ctx->ev[ev++], st);
   B200_TRY(msm_join(ctx));
   DeltaMultiples dm;
   if (!pk->partial) dm = delta_multiples(pk, r, s);  // host work hidden behind the GPU's
   B200_CUDA(cudaStreamSynchronize(st));
   *ev_io = ev;
+  const MsmCfg* cfg = ctx->prove_cfg;
 
   G1Affine A, B1, K, Z;
   G2Affine B2;
@@ -261,6 +269,19 @@ static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wire
   memcpy(out->msm_z, &Z, 64);
   memcpy(out->msm_b2, &B2, 128);
   return 0;
+}
+
+// abc_ready: event after which d_a, d_b, d_c are valid (the host path uploads them on the copy stream while
+// the four MSMs that only need the witness already run), or nullptr.
+// d_wires: n_wires Fr; d_a/b/c: N Fr each, zero padded. h is left in d_a.
+// d_b == nullptr: d_a already holds h (computeH was done elsewhere, e.g. spread over several GPUs).
+static int prove_device(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, Fr* d_a, Fr* d_b, Fr* d_c,
+                        const Fr& r, const Fr& s, b200g16_proof* out, int* ev_io, cudaEvent_t abc_ready = nullptr) {
+  B200_TRY(prove_front(ctx, pk, d_wires, ev_io));
+  if (abc_ready) B200_CUDA(cudaStreamWaitEvent(ctx->stream, abc_ready, 0));
+  if (d_b) B200_TRY(compute_h_device(ctx, d_a, d_b, d_c, (int)pk->log2n, false));
+  if (*ev_io < 18) cudaEventRecord(ctx->ev[(*ev_io)++], ctx->stream);
+  return prove_back(ctx, pk, d_a, r, s, out, ev_io);
 }
 
 }  // namespace b200
@@ -343,6 +364,35 @@ int b200g16_prove_h_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wi
   memcpy(&fr_r, r, 32);
   memcpy(&fr_s, s, 32);
   B200_TRY(prove_device(ctx, pk, (const Fr*)d_wires, (Fr*)d_h, nullptr, nullptr, fr_r, fr_s, proof_out, &ev));
+  ctx->timings.n = ev - 1;
+  for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
+  return 0;
+}
+
+int b200g16_prove_begin_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires) {
+  if (!ctx || !pk || !d_wires) return fail(B200G16_ERR_ARG, "prove_begin_dev: null");
+  if (pk->device != ctx->device) return fail(B200G16_ERR_STATE, "prove_begin_dev: pk lives on another device");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  int ev = 0;
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  cudaEventRecord(ctx->ev[ev++], ctx->stream);
+  B200_TRY(prove_front(ctx, pk, (const Fr*)d_wires, &ev));
+  ctx->timings.n = -(ev - 1);   // resolved by prove_end_dev
+  return 0;
+}
+
+int b200g16_prove_end_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_h, const uint64_t r[4],
+                          const uint64_t s[4], b200g16_proof* proof_out) {
+  if (!ctx || !pk || !d_h || !r || !s || !proof_out) return fail(B200G16_ERR_ARG, "prove_end_dev: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  int ev = ctx->timings.n < 0 ? 1 - ctx->timings.n : 0;
+  if (ev < 18) cudaEventRecord(ctx->ev[ev++], ctx->stream);   // everything the caller ran in between (computeH stages)
+  Fr fr_r, fr_s;
+  memcpy(&fr_r, r, 32);
+  memcpy(&fr_s, s, 32);
+  B200_TRY(prove_back(ctx, pk, (const Fr*)d_h, fr_r, fr_s, proof_out, &ev));
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   return 0;

@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200g16_prove_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_prove_h_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_h_pointwise_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint]),
+    "b200g16_prove_begin_dev": (C.c_int, [_vp, _vp, _vp]),
+    "b200g16_prove_end_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_prove_finish": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200g16_pairing_check": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(C.c_int)]),
     "b200g16_pair": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -478,6 +480,17 @@ class Context:
         r, s = _u64(r).reshape(4), _u64(s).reshape(4)
         out = ProofOut()
         _check(load().b200g16_prove_h_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
+        return out.as_dict()
+
+    def prove_begin_dev(self, pk, d_wires):
+        """First half of a prove: the four witness MSMs are enqueued; returns without waiting."""
+        _check(load().b200g16_prove_begin_dev(self.h, pk, _vp(int(d_wires))))
+
+    def prove_end_dev(self, pk, d_h, r, s):
+        """Second half: Z MSM over h (device pointer), wait, assemble."""
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        out = ProofOut()
+        _check(load().b200g16_prove_end_dev(self.h, pk, _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)

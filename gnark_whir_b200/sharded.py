@@ -28,6 +28,31 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_range_weighted(n, rank, weights):
+    """Contiguous [lo, hi) for `rank` with shard sizes proportional to `weights` (one per rank)."""
+    if not (0 <= rank < len(weights)):
+        raise ValueError("rank out of range")
+    tot = float(sum(weights))
+    cuts = [0]
+    acc = 0.0
+    for w in weights:
+        acc += w
+        cuts.append(min(n, int(round(n * acc / tot))))
+    cuts[-1] = n
+    return cuts[rank], cuts[rank + 1]
+
+
+def prove_weights(world, h_ranks_share=None):
+    """Relative MSM shard sizes for the sharded prove.  With world >= 3 the first three ranks also run
+    two of computeH's seven transforms each, so they get smaller point shards: share x < 1 such that
+    (transforms + x * msm) on those ranks ~ msm on the others.  h_ranks_share: x, or None for the
+    default tuned on the synthetic WHIR-shaped prove (bench.py --workload prove)."""
+    if world < 3:
+        return [1.0] * world
+    x = h_ranks_share if h_ranks_share is not None else {4: 0.78, 8: 0.55}.get(world, max(0.3, 1.0 - 3.6 / world))
+    return [x] * 3 + [1.0] * (world - 3)
+
+
 def combine_partials(partials, group=1):
     """Sum of affine partial results (iterable of uint64[8] / uint64[16]) -> affine."""
     add = lib.g1_add if group == 1 else lib.g2_add
@@ -137,6 +162,47 @@ def compute_h_distributed(ctx, t_a, t_b, t_c, log2n, pg=None):
     ctx.h_pointwise_dev(t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr(), log2n)
     ctx.ntt_dev(t_a.data_ptr(), log2n, inverse=True, coset=True, decimation=lib.DIF)
     return t_a
+
+
+def prove_distributed(ctx, pk_shard, t_wires, t_a, t_b, t_c, log2n, r, s, device=None, pg=None):
+    """One rank's part of a sharded prove with computeH spread over the ranks and overlapped with the
+    witness MSMs.  Tensors are torch int64 (n, 4) on this rank's GPU; a, b, c zero-padded, identical on all
+    ranks, clobbered.  Ranks that own a vector (h_vector_owner) transform it first, so the broadcasts can
+    start early, then enqueue their (smaller, see prove_weights) MSM shards; the other ranks enqueue their
+    MSMs first and meet the broadcast while those run.  Every rank then finishes h and runs Z.
+    Returns the finished proof dict (all ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(pg) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return ctx.prove_dev(pk_shard, t_wires.data_ptr(), t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr(), r, s)
+    rank = dist.get_rank(pg)
+    vecs = (t_a, t_b, t_c)
+    mine = [v for v in range(3) if h_vector_owner(v, world) == rank]
+    if not mine:
+        ctx.prove_begin_dev(pk_shard, t_wires.data_ptr())           # MSMs run while the owners transform
+    for v in mine:
+        ctx.ntt_dev(vecs[v].data_ptr(), log2n, inverse=True, decimation=lib.DIF)
+        ctx.ntt_dev(vecs[v].data_ptr(), log2n, coset=True, decimation=lib.DIT)
+    for v, t in enumerate(vecs):
+        src = h_vector_owner(v, world)
+        dist.broadcast(t, src=dist.get_global_rank(pg, src) if pg is not None else src, group=pg)
+    if mine:
+        ctx.prove_begin_dev(pk_shard, t_wires.data_ptr())
+    if t_a.is_cuda:
+        torch.cuda.current_stream().synchronize()                   # broadcasts landed before the library reads them
+    ctx.h_pointwise_dev(t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr(), log2n)
+    ctx.ntt_dev(t_a.data_ptr(), log2n, inverse=True, coset=True, decimation=lib.DIF)
+    part = ctx.prove_end_dev(pk_shard, t_a.data_ptr(), r, s)
+    packed = pack_partials(part)
+    t = torch.from_numpy(packed.view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=pg)
+    sums = sum_partials([o.cpu().numpy().view(np.uint64) for o in outs])
+    return ctx.prove_finish(pk_shard, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], r, s)
 
 
 class ShardedBases:

@@ -342,6 +342,15 @@ int b200g16_g2_decode(b200g16_ctx* ctx, const uint8_t* in, size_t n, int raw, in
 int b200g16_g1_encode(b200g16_ctx* ctx, const uint64_t* points, size_t n, int raw, uint8_t* out);
 int b200g16_g2_encode(b200g16_ctx* ctx, const uint64_t* points, size_t n, int raw, uint8_t* out);
 
+/* A prove in two halves, for callers that compute h elsewhere while the witness MSMs already run (the
+ * multi-GPU prove: sharded.prove_distributed).  begin: gathers + MSM B2, B1, A, K enqueued on the ctx's
+ * streams, returns WITHOUT waiting.  end: MSM Z over d_h (N elements, bit-reversed), waits, assembles
+ * the proof (or, for a partial pk, the five partial sums).  One prove in flight per ctx; d_wires must
+ * stay valid until end returns; other calls on the ctx in between queue behind the MSMs. */
+int b200g16_prove_begin_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires);
+int b200g16_prove_end_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_h, const uint64_t r[4],
+                          const uint64_t s[4], b200g16_proof* proof_out);
+
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);

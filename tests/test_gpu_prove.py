@@ -160,6 +160,15 @@ def test_staged_compute_h_and_prove_h_match_prove(ctx):
         staged = ctx.prove_h_dev(pk.device_handle(ctx), wires.data_ptr(), ta.data_ptr(), fr[4], fr[5])
         for k in full:
             assert np.array_equal(full[k], staged[k]), k
+        # the two-halves form: witness MSMs enqueued first, h supplied later (other library calls in between)
+        ctx.prove_begin_dev(pk.device_handle(ctx), wires.data_ptr())
+        tb3 = dev(fr[2])
+        ctx.ntt_dev(tb3.data_ptr(), L, inverse=True, decimation=lib.DIF)      # queues behind the MSMs
+        halves = ctx.prove_end_dev(pk.device_handle(ctx), ta.data_ptr(), fr[4], fr[5])
+        for k in full:
+            assert np.array_equal(full[k], halves[k]), k
+        with pytest.raises(lib.B200Error):                                    # end without begin
+            ctx.prove_end_dev(pk.device_handle(ctx), ta.data_ptr(), fr[4], fr[5])
     finally:
         pk.free()
 
