@@ -217,13 +217,17 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   const int spar = reuse ? ls.par : par;  // set holding the sorted state: counts, offsets, tasks, totals
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
   B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
-  B200_TRY(ws.counts[spar].ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
   // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
   const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
-  B200_TRY(ws.misc[spar].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
-  B200_TRY(ws.tasks[spar].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
-  B200_TRY(ws.partials[par].ensure(max_tasks * sizeof(XYZZ<F>)));
-  B200_TRY(ws.chunks[par].ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
+  // every rotating set is sized for this call at once: a prove alternates G1 and G2 MSMs over the sets, and
+  // growing a set later would cost a cudaFree (device-wide synchronisation) in the middle of a prove
+  for (int q = 0; q < MSM_SETS; q++) {
+    B200_TRY(ws.counts[q].ensure((size_t)cfg.nb * 4 * sizeof(uint32_t)));  // counts, offsets, cursor, task_off
+    B200_TRY(ws.misc[q].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
+    B200_TRY(ws.tasks[q].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
+    B200_TRY(ws.partials[q].ensure(max_tasks * sizeof(XYZZ<F>)));
+    B200_TRY(ws.chunks[q].ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
+  }
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
   if (ws.pinned_cap < MSM_SLOTS * slot_bytes) {
     if (ws.pinned) cudaFreeHost(ws.pinned);
