@@ -130,7 +130,7 @@ struct b200g16_ctx {
   cudaEvent_t ev_copy[4] = {};
   cudaEvent_t ev_front[b200::MSM_SETS] = {}, ev_tail[b200::MSM_SETS] = {};
   bool tail_pending[b200::MSM_SETS] = {};
-  int msm_parity = 0;
+  int msm_parity = 0;               // next rotating buffer set (0 .. MSM_SETS-1)
   b200::MsmSorted last_sort;
   // a prove between its two halves (b200g16_prove_begin_dev / _end_dev): decompositions of the five MSMs
   b200::MsmCfg prove_cfg[5] = {};

@@ -8,17 +8,22 @@
 //
 //   k_digits      scalar Montgomery->canonical, signed c-bit digits (partitionScalars' job),
 //                 per-(window,bucket) histogram
-//   k_scan        exclusive scan of the histogram -> entry offsets; buckets larger than `seg`
+//   k_scan_*      exclusive scan of the histogram -> entry offsets; buckets larger than `seg`
 //                 are split into several tasks (0/1-heavy witnesses put millions of points in
 //                 bucket "1" of window 0) -> task offsets
-//   k_scatter     window-major counting-sort scatter of (point index, sign) into bucket order;
+//   k_scatter     window-major counting-sort scatter of (entry index, sign) into bucket order;
 //                 one window's 4n bytes of targets stay resident in the 126 MB L2
-//   k_tasks       task -> bucket table
+//   k_tasks, k_task_*  task -> bucket table; tasks ordered by length so a warp's lanes finish together
 //   k_accumulate  one thread per task: gathers its affine points with 128-bit loads, mixed
 //                 XYZZ adds (10 modmul) on the integer pipe; next point prefetched during the add
-//   k_merge(+heavy) sums the partials of split buckets
-//   k_reduce / k_reduce2  running-sum bucket reduction per window, in chunks, then a block tree
-//   host          Horner over the W window sums + one inversion -> affine
+//   ---- "tail", on a second stream under the next MSM's work above ----
+//   k_merge_pass  fan-in-4 tree over the partials of split buckets
+//   k_reduce, k_sum_pass  running-sum bucket reduction in chunks, then fan-in-4 plain sums per window
+//   host          Horner over the window sums + one inversion -> affine
+//
+// With a window table over the bases (b200g16_bases_precompute: row k = 2^(ck) P_i) all digits address
+// ONE bucket set, entries index the table, and the host has no Horner to do.  A following MSM over the
+// same scalars and decomposition can reuse the sorted lists (share_sort: groth16's Bs1 after Bs2).
 #pragma once
 #include "common.cuh"
 #include "ec.cuh"
