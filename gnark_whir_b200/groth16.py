@@ -153,6 +153,8 @@ class VerifyingKey:                # groth16_bn254.VerifyingKey
     PedersenGSigmaNeg: np.ndarray = None
     PublicAndCommitmentCommitted: list = field(default_factory=list)
     has_commitment: bool = False
+    G1_Beta: np.ndarray = None     # carried by gnark's vk and its wire format; Verify does not use them
+    G1_Delta: np.ndarray = None
 
 
 @dataclass
@@ -193,6 +195,64 @@ def proof_read_from(ctx, data, raw=False):
     if not (ok1.all() and ok2.all()):
         raise ValueError("groth16.Proof.ReadFrom: invalid point encoding")
     return Proof(g1[0], g1[1], g2[0], [g1[2 + i] for i in range(k)], g1[2 + k])
+
+
+def vk_write_to(ctx, vk, raw=False):
+    """(*VerifyingKey).WriteTo / WriteRawTo -> bytes (gnark backend/groth16/bn254/marshal.go, as recalled):
+    G1.Alpha | G1.Beta | G2.Beta | G2.Gamma | G1.Delta | G2.Delta | u32 len(K) | K... |
+    PublicAndCommitmentCommitted as [][]uint64 (u32 outer length, then u32 length + big-endian u64s each) |
+    u32 #commitment keys | per key: pedersen G | GSigmaNeg (G2)."""
+    zero1 = np.zeros(8, dtype=np.uint64)
+    g1 = np.stack([np.asarray(p if p is not None else zero1, dtype=np.uint64).reshape(8)
+                   for p in [vk.G1_Alpha, vk.G1_Beta, vk.G1_Delta]] + [np.asarray(k, dtype=np.uint64).reshape(8) for k in vk.G1_K])
+    g2_list = [vk.G2_Beta, vk.G2_Gamma, vk.G2_Delta] + ([vk.PedersenG, vk.PedersenGSigmaNeg] if vk.has_commitment else [])
+    e1 = ctx.encode_points(g1, group=1, raw=raw)
+    e2 = ctx.encode_points(np.stack([np.asarray(q, dtype=np.uint64).reshape(16) for q in g2_list]), group=2, raw=raw)
+    out = e1[0].tobytes() + e1[1].tobytes() + e2[0].tobytes() + e2[1].tobytes() + e1[2].tobytes() + e2[2].tobytes()
+    out += len(vk.G1_K).to_bytes(4, "big") + b"".join(e1[3 + i].tobytes() for i in range(len(vk.G1_K)))
+    groups = [list(vk.PublicAndCommitmentCommitted)] if vk.has_commitment else []
+    out += len(groups).to_bytes(4, "big")
+    for g in groups:
+        out += len(g).to_bytes(4, "big") + b"".join(int(x).to_bytes(8, "big") for x in g)
+    out += (1 if vk.has_commitment else 0).to_bytes(4, "big")
+    if vk.has_commitment:
+        out += e2[3].tobytes() + e2[4].tobytes()
+    return out
+
+
+def vk_read_from(ctx, data, raw=False):
+    """(*VerifyingKey).ReadFrom -> VerifyingKey; raises ValueError on an invalid encoding."""
+    s1, s2 = (64, 128) if raw else (32, 64)
+    o = 0
+
+    def take(k):
+        nonlocal o
+        if o + k > len(data):
+            raise ValueError("groth16.VerifyingKey.ReadFrom: short buffer")
+        v = data[o:o + k]
+        o += k
+        return v
+    a1, b1, b2, g2, d1, d2 = take(s1), take(s1), take(s2), take(s2), take(s1), take(s2)
+    nk = int.from_bytes(take(4), "big")
+    kbytes = take(nk * s1)
+    groups = []
+    for _ in range(int.from_bytes(take(4), "big")):
+        m = int.from_bytes(take(4), "big")
+        groups.append([int.from_bytes(take(8), "big") for _ in range(m)])
+    nck = int.from_bytes(take(4), "big")
+    if nck > 1 or nck != len(groups):
+        raise ValueError("groth16.VerifyingKey.ReadFrom: this backend supports at most one commitment")
+    ped = take(2 * s2) if nck else b""
+    p1, ok1 = ctx.decode_points(a1 + b1 + d1 + kbytes, group=1, raw=raw)
+    p2, ok2 = ctx.decode_points(b2 + g2 + d2 + ped, group=2, raw=raw)
+    if not (ok1.all() and ok2.all()):
+        raise ValueError("groth16.VerifyingKey.ReadFrom: invalid point encoding")
+    vk = VerifyingKey(p1[0], p1[3:3 + nk], p2[0], p2[1], p2[2], G1_Beta=p1[1], G1_Delta=p1[2])
+    if nck:
+        vk.PedersenG, vk.PedersenGSigmaNeg = p2[3], p2[4]
+        vk.PublicAndCommitmentCommitted = groups[0]
+        vk.has_commitment = True
+    return vk
 
 
 @dataclass
@@ -301,7 +361,7 @@ def Setup(ctx, r1cs, toxic=None):
     pkB2 = pts2[:len(sb)].copy()
     beta2, delta2, gamma2 = pts2[len(sb)], pts2[len(sb) + 1], pts2[len(sb) + 2]
     pk = ProvingKey(logn, alpha1, beta1, delta1, pkA, pkB, pkZ, pkK, beta2, delta2, pkB2, inf_a, inf_b, k_skip)
-    vk = VerifyingKey(alpha1, vkK, beta2, gamma2, delta2)
+    vk = VerifyingKey(alpha1, vkK, beta2, gamma2, delta2, G1_Beta=beta1, G1_Delta=delta1)
     if r1cs.commitment_wire >= 0:
         # pedersen.Setup: BasisExpSigma = sigma * Basis; vk = (G, -sigma * G)
         bes = ctx.fixed_base_mul(g1, fr_array([k * tw.sigma % R_MOD for k in k_ped]), group=1)

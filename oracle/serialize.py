@@ -12,6 +12,9 @@ Point encodings (big-endian field elements, 2 flag bits in the most significant 
 G1: X is 32 bytes.  G2: X = X.A1 || X.A0 (64 bytes), Y likewise; "largest" compares A1 first, then A0.
 Slices: uint32 big-endian length, then the elements.
 Proof: Ar (G1) | Bs (G2) | Krs (G1) | len(Commitments) u32 | Commitments... (G1) | CommitmentPok (G1).
+VerifyingKey: G1.Alpha | G1.Beta | G2.Beta | G2.Gamma | G1.Delta | G2.Delta | u32 len(K) | K... |
+  PublicAndCommitmentCommitted [][]uint64 (u32 outer len; per group u32 len + big-endian u64s) |
+  u32 #commitment keys | per key: pedersen G | GSigmaNeg (G2).
 Parity is UNPINNED by the reference (no vectors on disk); pins here are algebraic (round trips, on-curve,
 sign rule) — see tests/test_oracle_cpu.py.
 """
@@ -167,3 +170,18 @@ def proof_read(buf):
         coms.append(c)
     pok, n = g1_set_bytes(buf[o:]); o += n
     return ar, bs, krs, coms, pok, o
+
+
+# ---------------------------------------------------------------- groth16 VerifyingKey
+def vk_write(alpha1, beta1, beta2, gamma2, delta1, delta2, K, committed_groups, pedersen_keys, raw=False):
+    """committed_groups: list of lists of wire ids; pedersen_keys: list of (G, GSigmaNeg) G2 pairs."""
+    e1, e2 = (g1_raw_bytes, g2_raw_bytes) if raw else (g1_bytes, g2_bytes)
+    out = e1(alpha1) + e1(beta1) + e2(beta2) + e2(gamma2) + e1(delta1) + e2(delta2)
+    out += len(K).to_bytes(4, "big") + b"".join(e1(k) for k in K)
+    out += len(committed_groups).to_bytes(4, "big")
+    for g in committed_groups:
+        out += len(g).to_bytes(4, "big") + b"".join(int(x).to_bytes(8, "big") for x in g)
+    out += len(pedersen_keys).to_bytes(4, "big")
+    for g, gs in pedersen_keys:
+        out += e2(g) + e2(gs)
+    return out

@@ -103,3 +103,37 @@ def test_decode_large_batch_matches_encode(ctx):
     enc = ctx.encode_points(pts, group=1)
     dec, ok = ctx.decode_points(enc, group=1)
     assert ok.all() and np.array_equal(dec, pts)
+
+
+@pytest.mark.parametrize("with_commitment", [False, True])
+@pytest.mark.parametrize("raw", [False, True])
+def test_verifying_key_wire_format(ctx, raw, with_commitment):
+    """Setup's vk through vk_write_to: byte-exact with the oracle's layout, and vk_read_from gives back a key
+    that verifies a proof made with the original."""
+    from oracle import groth16 as og
+    rng = random.Random(53)
+    r1cs, w = og.synthetic_r1cs(20, 3, rng, with_commitment=with_commitment)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    pk, vk = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    try:
+        _, ovk = og.setup(r1cs, tw)
+        data = g16.vk_write_to(ctx, vk, raw=raw)
+        exp = ser.vk_write(ovk.alpha1, bn.g1_mul(bn.G1_GEN, tw.beta), ovk.beta2, ovk.gamma2,
+                           bn.g1_mul(bn.G1_GEN, tw.delta), ovk.delta2, ovk.K,
+                           [list(ovk.public_committed)] if with_commitment else [],
+                           [(ovk.ped_g, ovk.ped_g_sigma_neg)] if with_commitment else [], raw=raw)
+        assert data == exp
+        back = g16.vk_read_from(ctx, data, raw=raw)
+        for f in ("G1_Alpha", "G1_K", "G2_Beta", "G2_Gamma", "G2_Delta", "G1_Beta", "G1_Delta"):
+            assert np.array_equal(getattr(back, f), getattr(vk, f)), f
+        assert back.has_commitment == with_commitment
+
+        def resolve(wit):
+            L, Rr, O = r1cs.constraints[-1]
+            wit[O[0][0]] = og.lc_eval(L, wit) * og.lc_eval(Rr, wit) % R
+        proof = g16.Prove(ctx, r1cs, pk, w, resolve=resolve if with_commitment else None)
+        g16.Verify(ctx, proof, back, proof.debug["witness"][1:r1cs.nb_public])
+        with pytest.raises(ValueError):
+            g16.vk_read_from(ctx, data[:-3], raw=raw)
+    finally:
+        pk.free()
