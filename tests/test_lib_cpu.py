@@ -144,3 +144,21 @@ def test_host_mirror_layout_and_hash_agree_with_oracle(rng):
     # Verify needs a device context: no CPU fallback behind the host mirror
     with pytest.raises(AttributeError):
         g16.Verify(None, g16.Proof(None, None, None), g16.VerifyingKey(None, None, None, None, None), [])
+
+
+def test_header_is_valid_c_and_library_refuses_to_run_without_a_gpu(tmp_path):
+    """include/b200g16.h compiled as plain C11 (what cgo does), linked against the built library, run:
+    host-only helpers answer, b200g16_init fails loudly without a device (no CPU fallback)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    libdir = os.path.join(root, "gnark_whir_b200")
+    exe = str(tmp_path / "abi_check")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(here, "host_harness", "abi_check.c"), "-L", libdir, "-lb200g16",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    import torch
+    if not torch.cuda.is_available():
+        assert out.stdout.startswith("nogpu:") and "no CPU fallback" in out.stdout
