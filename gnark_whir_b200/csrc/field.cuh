@@ -177,6 +177,92 @@ struct alignas(16) Field {
     reduce_once(r);
     return r;
   }
+  // ---- Montgomery square ---------------------------------------------------------------
+  // a^2 = sum_i a_i 2^(32i) * V_i with V_i = a_i 2^(32i) + 2 * (a with limbs 0..i cleared): row i of the
+  // word-serial product above multiplies the word a_i by the limbs of V_i, whose limbs below i are zero, so
+  // those partial products become plain carry propagation (IADD3.X on the otherwise idle ALU pipe):
+  // 36 + 72 = 108 wide multiply-adds instead of 136.  Limbs of V_i: j = i: a_i; j = i+1: a_j << 1;
+  // j > i+1: (a_j << 1) | (a_(j-1) >> 31)  (a < 2^254, so nothing is shifted out at the top).
+  // Bounds: V_i < 2^255, hence every intermediate accumulator stays below 2^255 + 2^254 < 2^256 and the
+  // result below 2p, as for the product.
+  template <bool Z> static B200_HD uint32_t zmad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+    return Z ? ptx::add_cc(c, 0) : ptx::mad_lo_cc(a, b, c);
+  }
+  template <bool Z> static B200_HD uint32_t zmadc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+    return Z ? ptx::addc_cc(c, 0) : ptx::madc_lo_cc(a, b, c);
+  }
+  template <bool Z> static B200_HD uint32_t zmadc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+    return Z ? ptx::addc_cc(c, 0) : ptx::madc_hi_cc(a, b, c);
+  }
+  template <bool Z> static B200_HD uint32_t zmadc_hi(uint32_t a, uint32_t b, uint32_t c) {
+    return Z ? ptx::addc(c, 0) : ptx::madc_hi(a, b, c);
+  }
+  // cmad_n / madc_n_rshift over an operand whose limbs below S are zero (OFF = 0: even limbs, 1: odd limbs)
+  template <int S, int OFF>
+  static B200_HD void cmad_n_from(uint32_t* acc, const uint32_t* v, uint32_t bi) {
+    acc[0] = zmad_lo_cc<(OFF < S)>(v[OFF], bi, acc[0]);
+    acc[1] = zmadc_hi_cc<(OFF < S)>(v[OFF], bi, acc[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      acc[j] = (j + OFF < S) ? ptx::addc_cc(acc[j], 0) : ptx::madc_lo_cc(v[j + OFF], bi, acc[j]);
+      acc[j + 1] = (j + OFF < S) ? ptx::addc_cc(acc[j + 1], 0) : ptx::madc_hi_cc(v[j + OFF], bi, acc[j + 1]);
+    }
+  }
+  template <int S, int OFF>
+  static B200_HD void madc_n_rshift_from(uint32_t* acc, const uint32_t* v, uint32_t bi) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      acc[j] = (j + OFF < S) ? ptx::addc_cc(acc[j + 2], 0) : ptx::madc_lo_cc(v[j + OFF], bi, acc[j + 2]);
+      acc[j + 1] = (j + OFF < S) ? ptx::addc_cc(acc[j + 3], 0) : ptx::madc_hi_cc(v[j + OFF], bi, acc[j + 3]);
+    }
+    acc[N - 2] = zmadc_lo_cc<(N - 2 + OFF < S)>(v[N - 2 + OFF], bi, 0);
+    acc[N - 1] = zmadc_hi<(N - 2 + OFF < S)>(v[N - 2 + OFF], bi, 0);
+  }
+  // row I of the square: operand limbs v[j], j >= I (lower limbs are zero), word bi = a_I
+  template <int I>
+  static B200_HD void sqr_row_redc(uint32_t* lo, uint32_t* hi, const uint32_t* v, uint32_t bi) {
+    if (I == 0) {
+      mul_n(hi, v + 1, bi);
+      mul_n(lo, v, bi);
+    } else {
+      lo[0] = ptx::add_cc(lo[0], hi[1]);
+      madc_n_rshift_from<I, 1>(hi, v, bi);
+      cmad_n_from<I, 0>(lo, v, bi);
+      hi[N - 1] = ptx::addc(hi[N - 1], 0);
+    }
+    uint32_t mi = ptx::mul_lo(lo[0], T::INV);
+    cmad_mod<1>(hi, mi);
+    cmad_mod<0>(lo, mi);
+    hi[N - 1] = ptx::addc(hi[N - 1], 0);
+  }
+  template <int I>
+  static B200_HD void sqr_operand(uint32_t* v, const Field& a) {  // limbs of V_I at positions >= I
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      if (j < I) v[j] = 0;
+      else if (j == I) v[j] = a.l[j];
+      else if (j == I + 1) v[j] = a.l[j] << 1;
+      else v[j] = (a.l[j] << 1) | (a.l[j - 1] >> 31);
+    }
+  }
+  static B200_HD Field sqr_ptx(const Field& a) {
+    uint32_t even[N], odd[N], v[N];
+    sqr_operand<0>(v, a); sqr_row_redc<0>(even, odd, v, a.l[0]);
+    sqr_operand<1>(v, a); sqr_row_redc<1>(odd, even, v, a.l[1]);
+    sqr_operand<2>(v, a); sqr_row_redc<2>(even, odd, v, a.l[2]);
+    sqr_operand<3>(v, a); sqr_row_redc<3>(odd, even, v, a.l[3]);
+    sqr_operand<4>(v, a); sqr_row_redc<4>(even, odd, v, a.l[4]);
+    sqr_operand<5>(v, a); sqr_row_redc<5>(odd, even, v, a.l[5]);
+    sqr_operand<6>(v, a); sqr_row_redc<6>(even, odd, v, a.l[6]);
+    sqr_operand<7>(v, a); sqr_row_redc<7>(odd, even, v, a.l[7]);
+    Field r;
+    r.l[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r.l[i] = ptx::addc_cc(even[i], odd[i + 1]);
+    r.l[N - 1] = ptx::addc(even[N - 1], 0);
+    reduce_once(r);
+    return r;
+  }
 #if !defined(__CUDA_ARCH__)
   // Host multiplier: 4 x 64-bit CIOS on unsigned __int128 (the host finishes every MSM with a
   // Horner pass and the proof with a handful of scalar multiplications).
@@ -234,7 +320,13 @@ struct alignas(16) Field {
     return mul_host64(a, b);
 #endif
   }
-  static B200_HD Field sqr(const Field& a) { return mul(a, a); }
+  static B200_HD Field sqr(const Field& a) {
+#if defined(__CUDA_ARCH__)
+    return sqr_ptx(a);
+#else
+    return mul(a, a);
+#endif
+  }
 
   // Out-of-line product, operands and result by value (registers): one copy of the multiplier
   // shared by every call site.  Used by Fp2 so that the G2 kernels stay small and keep their

@@ -84,6 +84,8 @@ extern "C" {
 void fp_mul_ptx(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::mul_ptx(x, y)); }
 void fr_mul_ptx(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; ld(x, a); ld(y, b); st(r, Fr::mul_ptx(x, y)); }
 void fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::mul(x, y)); }
+void fp_sqr_ptx(const uint32_t* a, uint32_t* r) { Fp x; ld(x, a); st(r, Fp::sqr_ptx(x)); }
+void fr_sqr_ptx(const uint32_t* a, uint32_t* r) { Fr x; ld(x, a); st(r, Fr::sqr_ptx(x)); }
 void fp_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::add(x, y)); }
 void fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::sub(x, y)); }
 void fp_neg(const uint32_t* a, uint32_t* r) { Fp x; ld(x, a); st(r, Fp::neg(x)); }
@@ -118,11 +120,16 @@ def test_device_montgomery_algorithm_pinned(fieldlib, rng):
             a, b = rng.randrange(P), rng.randrange(P)
         fieldlib.fp_mul_ptx(_limbs(a), _limbs(b), o); assert _val(o) == a * b * rip % P
         fieldlib.fp_mul(_limbs(a), _limbs(b), o); assert _val(o) == a * b * rip % P
+        fieldlib.fp_sqr_ptx(_limbs(a), o); assert _val(o) == a * a * rip % P      # the device's dedicated square
+        fieldlib.fr_sqr_ptx(_limbs(b % R), o); assert _val(o) == (b % R) ** 2 * rir % R
         fieldlib.fp_add(_limbs(a), _limbs(b), o); assert _val(o) == (a + b) % P
         fieldlib.fp_sub(_limbs(a), _limbs(b), o); assert _val(o) == (a - b) % P
         fieldlib.fp_neg(_limbs(a), o); assert _val(o) == (-a) % P
         a %= R; b %= R
         fieldlib.fr_mul_ptx(_limbs(a), _limbs(b), o); assert _val(o) == a * b * rir % R
+    for a in [(1 << 253), (1 << 253) + 0xffffffff, P >> 1, 0xffffffff, (P - 1) & ~0xffffffff,
+              sum(0x80000000 << (32 * k) for k in range(7))]:      # every limb's top bit set: the doubled operand's carries
+        fieldlib.fp_sqr_ptx(_limbs(a % P), o); assert _val(o) == (a % P) ** 2 * rip % P
     a = rng.randrange(1, P)
     fieldlib.fp_inv(_limbs(a * (1 << 256) % P), o); assert _val(o) * rip % P == pow(a, -1, P)
     a = rng.randrange(1, R)
