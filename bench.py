@@ -30,7 +30,9 @@ sys.path.insert(0, ROOT)
 SEED = 20261018
 MAD_PER_MODMUL = 136          # 2*8*8 + 8 32x32 multiply-adds per Montgomery product
 MODMUL_PER_MADD = 10          # XYZZ mixed add: 8M + 2S
-EXECUTED_MAD_PER_MADD = 8 * 136 + 2 * 108   # the two squares run the 108-MAD dedicated square (field.cuh sqr_ptx)
+# executed by k_accumulate per mixed add: 6 products, 2 dedicated squares (sqr_ptx: 108), and y3 = R(Q-X3) - Y*PPP
+# as one fused two-term product (dot2_ptx: 200 instead of 2 x 136)
+EXECUTED_MAD_PER_MADD = 6 * 136 + 2 * 108 + 200
 
 
 def rand_fr(rs, n):
@@ -263,8 +265,9 @@ def run_b200(args, rank, local_rank, world):
                 "algorithmic_mads_per_launch": int(mads), "window_bits": win_c, "adds_per_point": win_W,
                 "frac_executed": round(ach * EXECUTED_MAD_PER_MADD / (MODMUL_PER_MADD * MAD_PER_MODMUL) / tmad_peak, 4),
                 "accumulate_ms": round(acc_ms, 4), "msm_device_ms": round(msm_dev_ms, 4),
-                "note": "achieved counts SURVEY's algorithmic 1360 multiply-adds per mixed add; the kernel executes 1304 "
-                        "(dedicated Montgomery square), frac_executed is the pipe's own utilisation.  "
+                "note": "achieved counts SURVEY's algorithmic 1360 multiply-adds per mixed add; the kernel executes 1232 "
+                        "(dedicated Montgomery square, fused two-term product), frac_executed is the pipe's own "
+                        "utilisation.  "
                         "north_star: MSM is judged against the integer pipe (no dense contraction, 96 B/point of HBM "
                         "traffic against ~20k multiply-adds/point); the HBM view is roofline_hbm"}
     roofline_hbm = {"bound": "hbm", "kernel": "k_accumulate<Fp>", "achieved": round(algo_bytes / (acc_ms * 1e6), 2),

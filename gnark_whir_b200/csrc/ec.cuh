@@ -21,13 +21,20 @@ struct alignas(16) Fp2 {
   static B200_HD Fp2 sub(const Fp2& a, const Fp2& b) { return {Fp::sub(a.c0, b.c0), Fp::sub(a.c1, b.c1)}; }
   static B200_HD Fp2 dbl(const Fp2& a) { return {Fp::dbl(a.c0), Fp::dbl(a.c1)}; }
   static B200_HD Fp2 neg(const Fp2& a) { return {Fp::neg(a.c0), Fp::neg(a.c1)}; }
-  // Karatsuba: 3 base-field products
+  // device: (a0 b0 - a1 b1) + (a0 b1 + a1 b0) u as two fused two-term products (2 x 200 multiply-adds, no
+  // field additions: the G2 kernels are limited by the ALU work around their products);
+  // host: Karatsuba, 3 base-field products
   static B200_HD Fp2 mul(const Fp2& a, const Fp2& b) {
+#if defined(__CUDA_ARCH__)
+    return {Fp::mul_sub_call(a.c0, b.c0, a.c1, b.c1), Fp::mul_add_call(a.c0, b.c1, a.c1, b.c0)};
+#else
     Fp t0 = Fp::mul_call(a.c0, b.c0);
     Fp t1 = Fp::mul_call(a.c1, b.c1);
     Fp t2 = Fp::mul_call(Fp::add(a.c0, a.c1), Fp::add(b.c0, b.c1));
     return {Fp::sub(t0, t1), Fp::sub(Fp::sub(t2, t0), t1)};
+#endif
   }
+  static B200_HD Fp2 mul_sub(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) { return sub(mul(a, b), mul(c, d)); }
   // (a0+a1)(a0-a1) + 2 a0 a1 u : 2 products
   static B200_HD Fp2 sqr(const Fp2& a) {
     Fp t0 = Fp::mul_call(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1));
@@ -68,7 +75,7 @@ struct alignas(16) XYZZ {
     F M = F::add(F::dbl(X2), X2);
     XYZZ r;
     r.x = F::sub(F::sqr(M), F::dbl(S));
-    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.y = F::mul_sub(M, F::sub(S, r.x), W, p.y);
     r.zz = V;
     r.zzz = W;
     return r;
@@ -83,7 +90,7 @@ struct alignas(16) XYZZ {
     F X2 = F::sqr(x);
     F M = F::add(F::dbl(X2), X2);
     F X3 = F::sub(F::sqr(M), F::dbl(S));
-    F Y3 = F::sub(F::mul(M, F::sub(S, X3)), F::mul(W, y));
+    F Y3 = F::mul_sub(M, F::sub(S, X3), W, y);
     x = X3;
     y = Y3;
     zz = F::mul(V, zz);
@@ -108,7 +115,7 @@ struct alignas(16) XYZZ {
     F PPP = F::mul(Pq, PP);
     F Q = F::mul(x, PP);
     F X3 = F::sub(F::sub(F::sqr(Rq), PPP), F::dbl(Q));
-    y = F::sub(F::mul(Rq, F::sub(Q, X3)), F::mul(y, PPP));
+    y = F::mul_sub(Rq, F::sub(Q, X3), y, PPP);
     x = X3;
     zz = F::mul(zz, PP);
     zzz = F::mul(zzz, PPP);
@@ -133,7 +140,7 @@ struct alignas(16) XYZZ {
     F PPP = F::mul(Pq, PP);
     F Q = F::mul(U1, PP);
     F X3 = F::sub(F::sub(F::sqr(Rq), PPP), F::dbl(Q));
-    y = F::sub(F::mul(Rq, F::sub(Q, X3)), F::mul(S1, PPP));
+    y = F::mul_sub(Rq, F::sub(Q, X3), S1, PPP);
     x = X3;
     zz = F::mul(F::mul(zz, q.zz), PP);
     zzz = F::mul(F::mul(zzz, q.zzz), PPP);

@@ -85,6 +85,8 @@ void fp_mul_ptx(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld
 void fr_mul_ptx(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; ld(x, a); ld(y, b); st(r, Fr::mul_ptx(x, y)); }
 void fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::mul(x, y)); }
 void fp_sqr_ptx(const uint32_t* a, uint32_t* r) { Fp x; ld(x, a); st(r, Fp::sqr_ptx(x)); }
+void fp_dot2_ptx(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  Fp x, y, z, w; ld(x, a); ld(y, b); ld(z, c); ld(w, d); st(r, Fp::dot2_ptx(x, y, z, w)); }
 void fr_sqr_ptx(const uint32_t* a, uint32_t* r) { Fr x; ld(x, a); st(r, Fr::sqr_ptx(x)); }
 void fp_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::add(x, y)); }
 void fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; ld(x, a); ld(y, b); st(r, Fp::sub(x, y)); }
@@ -121,6 +123,9 @@ def test_device_montgomery_algorithm_pinned(fieldlib, rng):
         fieldlib.fp_mul_ptx(_limbs(a), _limbs(b), o); assert _val(o) == a * b * rip % P
         fieldlib.fp_mul(_limbs(a), _limbs(b), o); assert _val(o) == a * b * rip % P
         fieldlib.fp_sqr_ptx(_limbs(a), o); assert _val(o) == a * a * rip % P      # the device's dedicated square
+        c, d = (P - 1 - it, P - 2) if it < 49 else (rng.randrange(P), rng.randrange(P))
+        fieldlib.fp_dot2_ptx(_limbs(a), _limbs(b), _limbs(c), _limbs(d), o)         # the device's fused a*b + c*d
+        assert _val(o) == (a * b + c * d) * rip % P
         fieldlib.fr_sqr_ptx(_limbs(b % R), o); assert _val(o) == (b % R) ** 2 * rir % R
         fieldlib.fp_add(_limbs(a), _limbs(b), o); assert _val(o) == (a + b) % P
         fieldlib.fp_sub(_limbs(a), _limbs(b), o); assert _val(o) == (a - b) % P
