@@ -17,6 +17,7 @@ template <class F>
 int fixed_base_mul_device(b200g16_ctx* ctx, const Affine<F>& base, const Fr* d_scalars, size_t n, Affine<F>* d_out);
 int modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int iters, double* modmul_per_s, float* ms_out);
 int pipe_probe(b200g16_ctx* ctx, int mode, int blocks_per_sm, int iters, double* ops_per_s, float* ms_out);
+int fp52_probe(b200g16_ctx* ctx, int variant, int blocks_per_sm, int iters, double* modmul_per_s, float* ms_out);
 int ntt_device(b200g16_ctx* ctx, Fr* d_data, int L, int batch, bool inverse, bool coset, int decimation);
 int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
 int h_pointwise_device(b200g16_ctx* ctx, Fr* a, const Fr* b, const Fr* c, int L);
@@ -338,11 +339,19 @@ int b200g16_modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int it
 }
 
 int b200g16_pipe_probe(b200g16_ctx* ctx, int mode, int blocks_per_sm, int iters, double* ops_per_s, float* ms) {
-  if (!ctx || !ops_per_s || !ms || mode < 0 || mode > 5 || blocks_per_sm < 1 || iters < 1)
+  if (!ctx || !ops_per_s || !ms || mode < 0 || mode > 9 || blocks_per_sm < 1 || iters < 1)
     return fail(B200G16_ERR_ARG, "pipe_probe: bad arg");
   std::lock_guard<std::mutex> lock(ctx->mu);
   B200_CUDA(cudaSetDevice(ctx->device));
   return pipe_probe(ctx, mode, blocks_per_sm, iters, ops_per_s, ms);
+}
+
+int b200g16_fp52_probe(b200g16_ctx* ctx, int variant, int blocks_per_sm, int iters, double* modmul_per_s, float* ms) {
+  if (!ctx || !modmul_per_s || !ms || variant < 0 || variant > 5 || blocks_per_sm < 1 || iters < 1)
+    return fail(B200G16_ERR_ARG, "fp52_probe: bad arg");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return fp52_probe(ctx, variant, blocks_per_sm, iters, modmul_per_s, ms);
 }
 
 int b200g16_msm_g1(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const uint64_t* scalars, size_t n,

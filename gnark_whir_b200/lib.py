@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200g16_bases_from_scalars_g2": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "b200g16_modmul_probe": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "b200g16_pipe_probe": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "b200g16_fp52_probe": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "b200g16_msm_g1": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g2": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g1_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
@@ -276,6 +277,12 @@ class Context:
         rate = C.c_double()
         ms = C.c_float()
         _check(load().b200g16_pipe_probe(self.h, mode, blocks_per_sm, iters, C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
+
+    def fp52_probe(self, variant, blocks_per_sm=4, iters=2000):
+        rate = C.c_double()
+        ms = C.c_float()
+        _check(load().b200g16_fp52_probe(self.h, variant, blocks_per_sm, iters, C.byref(rate), C.byref(ms)))
         return rate.value, ms.value
 
     # -- NTT / computeH (mirror fft.Domain.FFT / FFTInverse and prove.go computeH)

@@ -171,8 +171,17 @@ int b200g16_modmul_probe(b200g16_ctx* ctx, int blocks_per_sm, int chains, int it
 /* Instruction-level probe: ops/s of one integer instruction class with 8 independent chains
  * per thread.  mode 0 IMAD (mad.lo.u32), 1 IMAD.WIDE (mad.wide.u32), 2 IMAD.WIDE.X carry
  * chains (mad.lo.cc/madc.hi.cc pairs, what the Montgomery multiplier issues), 3 IMAD.HI,
- * 4 IADD3.X carry chains, 5 modes 2 and 4 interleaved (reports the wide-MAD rate). */
+ * 4 IADD3.X carry chains, 5 modes 2 and 4 interleaved (reports the wide-MAD rate),
+ * 6 DFMA (fma.rz.f64), 7 DFMA + three-input 64-bit integer adds interleaved (reports the
+ * DFMA rate), 8 DFMA + IMAD.WIDE.X interleaved 1:1 (reports the rate of each), 9 DADD. */
 int b200g16_pipe_probe(b200g16_ctx* ctx, int mode, int blocks_per_sm, int iters, double* ops_per_s, float* ms);
+
+/* Whole Montgomery products per second of the FP64-pipe multiplier (csrc/fp52.cuh: 5 x 52-bit
+ * limbs in doubles, DFMA.RZ splitting) alone and next to the integer multiplier in the same
+ * thread.  variant 0/1/2: 1/2/4 DFMA chains; 3: 1 integer + 1 DFMA chain; 4: 1 integer + 2 DFMA
+ * chains; 5: 2 integer chains (same harness, for reference). */
+int b200g16_fp52_probe(b200g16_ctx* ctx, int variant, int blocks_per_sm, int iters, double* modmul_per_s,
+                       float* ms);
 
 /* ---- multi-scalar multiplication -------------------------------------------------- */
 /* out = sum_i scalars[i] * bases[offset + i], i < n.  Replaces gnark-crypto

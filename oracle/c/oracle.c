@@ -287,31 +287,40 @@ int oracle_msm_g1(const u64* points, const u64* scalars, size_t n, int threads, 
 
 /* points[i] = (k0 + i*d) * G for the generator (1,2): an arithmetic progression of known
  * discrete logs (cheap to make: one mixed add each + a batched normalisation). */
-int oracle_g1_progression(const u64* k0_mont, const u64* d_mont, size_t n, u64* out_points) {
-  g1a G; G.x = FP_ONE; fp_add(&G.y, &FP_ONE, &FP_ONE);
-  fe k0, dd; fr_from_mont(&k0, (const fe*)k0_mont); fr_from_mont(&dd, (const fe*)d_mont);
-  g1x P0, D; g1x_set_inf(&P0); g1x_set_inf(&D);
-  for (int i = 255; i >= 0; i--) {
-    g1x_dbl(&P0); g1x_dbl(&D);
-    if ((k0.l[i >> 6] >> (i & 63)) & 1) g1x_madd(&P0, &G, 0);
-    if ((dd.l[i >> 6] >> (i & 63)) & 1) g1x_madd(&D, &G, 0);
-  }
-  g1a Da; g1x_to_affine(&Da, &D);
-  g1x* jac = (g1x*)malloc(n * sizeof(g1x));
-  fe* pref = (fe*)malloc(n * sizeof(fe));
-  if (!jac || !pref) return -1;
-  g1x cur = P0;
-  for (size_t i = 0; i < n; i++) { jac[i] = cur; g1x_madd(&cur, &Da, 0); }
-  /* batch inversion of zzz */
+static void g1_progression_range(const g1a* G, const fe* k0, const fe* dd, const g1a* Da, size_t lo, size_t hi,
+                                 g1a* o, g1x* jac, fe* pref) {
+  /* start = (k0 + lo*d) * G by double-and-add, then one mixed add per point and a batched normalisation */
+  fe start = *k0, lo_fe, t; fr_from_u64(&lo_fe, (u64)lo); fr_mul(&t, &lo_fe, dd); fr_add(&start, &start, &t);
+  fe sc; fr_from_mont(&sc, &start);
+  g1x cur; g1x_set_inf(&cur);
+  for (int i = 255; i >= 0; i--) { g1x_dbl(&cur); if ((sc.l[i >> 6] >> (i & 63)) & 1) g1x_madd(&cur, G, 0); }
+  for (size_t i = lo; i < hi; i++) { jac[i] = cur; g1x_madd(&cur, Da, 0); }
   fe run = FP_ONE;
-  for (size_t i = 0; i < n; i++) { pref[i] = run; if (!fe_is_zero(&jac[i].zz)) fp_mul(&run, &run, &jac[i].zzz); }
+  for (size_t i = lo; i < hi; i++) { pref[i] = run; if (!fe_is_zero(&jac[i].zz)) fp_mul(&run, &run, &jac[i].zzz); }
   fe inv; fp_inv(&inv, &run);
-  g1a* o = (g1a*)out_points;
-  for (size_t i = n; i-- > 0;) {
+  for (size_t i = hi; i-- > lo;) {
     if (fe_is_zero(&jac[i].zz)) { memset(&o[i], 0, sizeof(g1a)); continue; }
     fe zi, a, izz; fp_mul(&zi, &inv, &pref[i]); fp_mul(&inv, &inv, &jac[i].zzz);
     fp_mul(&a, &jac[i].zz, &zi); fp_mul(&izz, &a, &a);
     fp_mul(&o[i].x, &jac[i].x, &izz); fp_mul(&o[i].y, &jac[i].y, &zi);
+  }
+}
+
+int oracle_g1_progression(const u64* k0_mont, const u64* d_mont, size_t n, u64* out_points) {
+  g1a G; G.x = FP_ONE; fp_add(&G.y, &FP_ONE, &FP_ONE);
+  const fe* k0 = (const fe*)k0_mont; const fe* dm = (const fe*)d_mont;
+  fe dd; fr_from_mont(&dd, dm);
+  g1x D; g1x_set_inf(&D);
+  for (int i = 255; i >= 0; i--) { g1x_dbl(&D); if ((dd.l[i >> 6] >> (i & 63)) & 1) g1x_madd(&D, &G, 0); }
+  g1a Da; g1x_to_affine(&Da, &D);
+  g1x* jac = (g1x*)malloc((n ? n : 1) * sizeof(g1x));
+  fe* pref = (fe*)malloc((n ? n : 1) * sizeof(fe));
+  if (!jac || !pref) return -1;
+  size_t chunk = 1 << 14, nchunks = (n + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t q = 0; q < nchunks; q++) {
+    size_t lo = q * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    g1_progression_range(&G, k0, dm, &Da, lo, hi, (g1a*)out_points, jac, pref);
   }
   free(jac); free(pref);
   return 0;
@@ -526,3 +535,5 @@ int oracle_threads(void) {
   return 1;
 #endif
 }
+
+#include "oracle_groth16.c"

@@ -49,6 +49,17 @@ def load():
         lib.oracle_merkle_paths.restype = None
         lib.oracle_merkle_paths.argtypes = [_vp, C.c_size_t, _vp, _vp, _vp, C.c_uint, C.c_size_t, _vp, C.c_int]
         lib.oracle_threads.restype = C.c_int
+        lib.oracle_msm_g2.restype = C.c_int
+        lib.oracle_msm_g2.argtypes = [_vp, _vp, C.c_size_t, C.c_int, _vp]
+        lib.oracle_g1_mul.restype = None
+        lib.oracle_g1_mul.argtypes = [_vp, _vp, _vp]
+        lib.oracle_g2_mul.restype = None
+        lib.oracle_g2_mul.argtypes = [_vp, _vp, _vp]
+        lib.oracle_g2_gen_mul.restype = None
+        lib.oracle_g2_gen_mul.argtypes = [_vp, _vp]
+        lib.oracle_groth16_prove.restype = C.c_int
+        lib.oracle_groth16_prove.argtypes = ([C.c_int, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t]
+                                             + [_vp] * 14 + [C.c_size_t, _vp, _vp, C.c_int, _vp, _vp])
         _lib = lib
     return _lib
 
@@ -147,3 +158,62 @@ def merkle_paths(leaves, siblings, auth_paths, indexes, nthreads=0):
     load().oracle_merkle_paths(_p(leaves), leaf_len, _p(siblings), _p(auth_paths), _p(indexes), height, n, _p(roots),
                                nthreads)
     return roots
+
+
+def msm_g2(points, scalars, nthreads=0):
+    pts, sc = _u64(points, 16), _u64(scalars, 4)
+    out = np.zeros(16, dtype=np.uint64)
+    if load().oracle_msm_g2(_p(pts), _p(sc), sc.shape[0], nthreads, _p(out)):
+        raise MemoryError("oracle_msm_g2")
+    return out
+
+
+def g1_mul(point, k_mont):
+    p, k = _u64(point, 8), _u64(k_mont, 4)
+    out = np.zeros(8, dtype=np.uint64)
+    load().oracle_g1_mul(_p(p), _p(k), _p(out))
+    return out
+
+
+def g2_mul(point, k_mont):
+    p, k = _u64(point, 16), _u64(k_mont, 4)
+    out = np.zeros(16, dtype=np.uint64)
+    load().oracle_g2_mul(_p(p), _p(k), _p(out))
+    return out
+
+
+def g2_gen_mul(k_mont):
+    k = _u64(k_mont, 4)
+    out = np.zeros(16, dtype=np.uint64)
+    load().oracle_g2_gen_mul(_p(k), _p(out))
+    return out
+
+
+PROVE_OUT = (("ar", 8), ("bs", 16), ("krs", 8), ("msm_a", 8), ("msm_b1", 8), ("msm_k", 8), ("msm_z", 8), ("msm_b2", 16))
+
+
+def groth16_prove(log2n, A, B1, K, Z, B2, alpha, beta, delta, beta2, delta2, infinity_a, infinity_b, k_skip,
+                  wires, a, b, c, r, s, nthreads=0, want_h=False):
+    """The C restatement of gnark's Prove after Solve (oracle_groth16_prove).  Arrays as in
+    gnark_whir_b200.lib.Context.pk_upload / prove.  Returns (dict of affine points, h or None)."""
+    A, B1, K, Z, B2 = _u64(A, 8), _u64(B1, 8), _u64(K, 8), _u64(Z, 8), _u64(B2, 16)
+    small = [_u64(alpha, 8), _u64(beta, 8), _u64(delta, 8), _u64(beta2, 16), _u64(delta2, 16)]
+    flags = [np.ascontiguousarray(f, dtype=np.uint8) for f in (infinity_a, infinity_b, k_skip)]
+    wires, a, b, c = _u64(wires, 4), _u64(a, 4), _u64(b, 4), _u64(c, 4)
+    r, s = _u64(r, 4), _u64(s, 4)
+    n = 1 << log2n
+    if Z.shape[0] != n - 1 or B2.shape[0] != B1.shape[0]:
+        raise ValueError("groth16_prove: Z must have N-1 points, B2 as many as B1")
+    out = np.zeros(80, dtype=np.uint64)
+    h = np.zeros((n, 4), dtype=np.uint64) if want_h else None
+    st = load().oracle_groth16_prove(log2n, wires.shape[0], _p(A), A.shape[0], _p(B1), B1.shape[0], _p(K), K.shape[0],
+                                     _p(Z), _p(B2), *[_p(x) for x in small], *[_p(f) for f in flags], _p(wires),
+                                     _p(a), _p(b), _p(c), a.shape[0], _p(r), _p(s), nthreads, _p(out),
+                                     _p(h) if want_h else None)
+    if st:
+        raise RuntimeError(f"oracle_groth16_prove: status {st}")
+    res, o = {}, 0
+    for k, w in PROVE_OUT:
+        res[k] = out[o:o + w].copy()
+        o += w
+    return res, h

@@ -194,6 +194,53 @@ def test_cport_msm_edge_cases(rng):
     assert not cport.msm_g1(np.zeros((0, 8), np.uint64), np.zeros((0, 4), np.uint64)).any()
 
 
+def test_cport_g2_msm_and_scalar_muls(rng):
+    ks = [rng.randrange(1, R) for _ in range(40)]
+    pts = [bn.g2_mul(bn.G2_GEN, k) for k in ks[:8]]
+    pts = (pts * 5) + [None, pts[0], bn.g2_neg(pts[1])]
+    ss = [rng.randrange(R) for _ in range(len(pts))]
+    ss[0], ss[1], ss[2], ss[-1], ss[-2] = 0, 1, R - 1, 5, 5
+    exp = bn.g2_msm(pts, ss)
+    for th in (1, 3):
+        assert bn.g2_from_array(cport.msm_g2(bn.g2_to_array(pts), bn.fr_to_mont_array(ss), th))[0] == exp
+    assert not cport.msm_g2(np.zeros((0, 16), np.uint64), np.zeros((0, 4), np.uint64)).any()
+    k = rng.randrange(R)
+    km = bn.fr_to_mont_array([k])
+    assert bn.g2_from_array(cport.g2_gen_mul(km))[0] == bn.g2_mul(bn.G2_GEN, k)
+    assert bn.g2_from_array(cport.g2_mul(bn.g2_to_array([pts[3]])[0], km))[0] == bn.g2_mul(pts[3], k)
+    p1 = bn.g1_mul(bn.G1_GEN, ks[9])
+    assert bn.g1_from_array(cport.g1_mul(bn.g1_to_array([p1])[0], km))[0] == bn.g1_mul(p1, k)
+
+
+@pytest.mark.parametrize("nb_constraints,nb_public", [(1, 1), (20, 3), (70, 5)])
+def test_cport_groth16_prove_matches_python_oracle(nb_constraints, nb_public):
+    """oracle_groth16_prove (the CPU baseline of the prove metric and the checker of the full-size GPU proves)
+    == oracle/groth16.py on every MSM output, h and the proof."""
+    rng = random.Random(1000 + nb_constraints)
+    r1cs, w = og.synthetic_r1cs(nb_constraints, nb_public, rng)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    pk, vk = og.setup(r1cs, tw)
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof, aux = og.prove(r1cs, pk, w, r, s)
+    k_skip = np.ones(r1cs.nb_wires, np.uint8)
+    k_skip[pk.k_wires] = 0
+    a, b, c = og.solve_abc(r1cs, w)
+    f = bn.fr_to_mont_array
+    got, h = cport.groth16_prove(
+        pk.domain.logn, bn.g1_to_array(pk.A), bn.g1_to_array(pk.B), bn.g1_to_array(pk.K), bn.g1_to_array(pk.Z),
+        bn.g2_to_array(pk.B2), bn.g1_to_array([pk.alpha1])[0], bn.g1_to_array([pk.beta1])[0],
+        bn.g1_to_array([pk.delta1])[0], bn.g2_to_array([pk.beta2])[0], bn.g2_to_array([pk.delta2])[0],
+        np.array(pk.infinity_a, np.uint8), np.array(pk.infinity_b, np.uint8), k_skip,
+        f(w), f(a), f(b), f(c), f([r])[0], f([s])[0], nthreads=2, want_h=True)
+    assert np.array_equal(h, f(aux["h"]))
+    assert bn.g1_from_array(got["ar"])[0] == proof.Ar
+    assert bn.g2_from_array(got["bs"])[0] == proof.Bs
+    assert bn.g1_from_array(got["krs"])[0] == proof.Krs
+    assert bn.g1_from_array(got["msm_z"])[0] == aux["krs2"]
+    gp = og.Proof(bn.g1_from_array(got["ar"])[0], bn.g2_from_array(got["bs"])[0], bn.g1_from_array(got["krs"])[0])
+    assert og.verify(gp, vk, w[:r1cs.nb_public])
+
+
 @pytest.mark.parametrize("logn", [0, 1, 4, 9])
 def test_cport_ntt_and_compute_h(rng, logn):
     n = 1 << logn
