@@ -77,6 +77,8 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
   if (offset > bases->n || n > bases->n - offset)
     return fail(B200G16_ERR_ARG, "msm: range [%zu,%zu) exceeds %zu bases", offset, offset + n, bases->n);
   std::lock_guard<std::mutex> lock(ctx->mu);
+  if (ctx->prove_active)   // the split prove's four pending MSMs own the result slots and the rotating buffer sets
+    return fail(B200G16_ERR_STATE, "msm: a prove is open on this ctx (b200g16_prove_begin_dev without _end_dev)");
   B200_CUDA(cudaSetDevice(ctx->device));
   MsmTable tab;
   const MsmTable* tp = nullptr;

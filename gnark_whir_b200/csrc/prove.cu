@@ -208,6 +208,7 @@ static int prove_enqueue_one(b200g16_ctx* ctx, const b200g16_pk* pk, int i, cons
 // Gathers + the four MSMs over witness values — G2 leading: its bucket reduction is the longest tail and
 // hides behind the G1 MSMs that follow.  Enqueues only; no synchronisation.
 static int prove_front(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, int* ev_io) {
+  if (ctx->prove_active) return fail(B200G16_ERR_STATE, "prove: another prove is already open on this ctx");
   cudaStream_t st = ctx->stream;
   int ev = *ev_io;
   auto mark = [&]() { if (ev < 18) cudaEventRecord(ctx->ev[ev++], st); };

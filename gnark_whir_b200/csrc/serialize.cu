@@ -97,16 +97,20 @@ __global__ void __launch_bounds__(128) k_g1_decode(const uint8_t* __restrict__ i
   const uint8_t flag = p[0] & M_MASK;
   G1Affine r = G1Affine::inf();
   bool ok = false;
-  if (flag == M_INFINITY) {
-    ok = all_zero(p, rec, true);
-  } else if (raw) {
+  if (raw) {
+    // bn254 has two flag bits only: the uncompressed point at infinity is flag 0b00 followed by zeros (X = Y = 0);
+    // 0b01 marks the COMPRESSED infinity (a compressed-size record) and has no place in a raw batch
     if (flag == M_UNCOMPRESSED) {
       Fp x = load_be(p, false), y = load_be(p + 32, false);
-      if (reduced(x) && reduced(y)) {
+      if (x.is_zero() && y.is_zero()) {
+        ok = true;
+      } else if (reduced(x) && reduced(y)) {
         r = {Fp::to_mont(x), Fp::to_mont(y)};
-        ok = g1_on_curve(r) && !r.is_inf();
+        ok = g1_on_curve(r);
       }
     }
+  } else if (flag == M_INFINITY) {
+    ok = all_zero(p, rec, true);
   } else if (flag != M_UNCOMPRESSED) {
     Fp x = load_be(p, true);
     if (reduced(x)) {
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(128) k_g1_encode(const G1Affine* __restrict__ 
   const G1Affine a = pts[i];
   if (a.is_inf()) {
     for (int k = 0; k < rec; k++) p[k] = 0;
-    p[0] = M_INFINITY;
+    if (!raw) p[0] = M_INFINITY;   // RawBytes() of infinity is all zero (flag 0b00)
     return;
   }
   store_be(p, Fp::from_mont(a.x));
@@ -150,16 +154,18 @@ __global__ void __launch_bounds__(128) k_g2_decode(const uint8_t* __restrict__ i
   const uint8_t flag = p[0] & M_MASK;
   G2Affine r = G2Affine::inf();
   bool ok = false;
-  if (flag == M_INFINITY) {
-    ok = all_zero(p, rec, true);
-  } else if (raw) {
+  if (raw) {
     if (flag == M_UNCOMPRESSED) {
       Fp x1 = load_be(p, false), x0 = load_be(p + 32, false), y1 = load_be(p + 64, false), y0 = load_be(p + 96, false);
-      if (reduced(x0) && reduced(x1) && reduced(y0) && reduced(y1)) {
+      if (x0.is_zero() && x1.is_zero() && y0.is_zero() && y1.is_zero()) {
+        ok = true;                 // uncompressed infinity: flag 0b00 + zeros
+      } else if (reduced(x0) && reduced(x1) && reduced(y0) && reduced(y1)) {
         r = {{Fp::to_mont(x0), Fp::to_mont(x1)}, {Fp::to_mont(y0), Fp::to_mont(y1)}};
-        ok = g2_on_curve(r) && !r.is_inf();
+        ok = g2_on_curve(r);
       }
     }
+  } else if (flag == M_INFINITY) {
+    ok = all_zero(p, rec, true);
   } else if (flag != M_UNCOMPRESSED) {
     Fp x1 = load_be(p, true), x0 = load_be(p + 32, false);
     if (reduced(x0) && reduced(x1)) {
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(128) k_g2_encode(const G2Affine* __restrict__ 
   const G2Affine a = pts[i];
   if (a.is_inf()) {
     for (int k = 0; k < rec; k++) p[k] = 0;
-    p[0] = M_INFINITY;
+    if (!raw) p[0] = M_INFINITY;
     return;
   }
   store_be(p, Fp::from_mont(a.x.c1));

@@ -143,6 +143,7 @@ int b200g16_verify(b200g16_ctx* ctx, const b200g16_vk_desc* vk, const uint64_t a
   if (n_public + 1 != vk->n_k)
     return fail(B200G16_ERR_ARG, "verify: %zu public inputs, vk.G1.K expects %zu", n_public, vk->n_k - 1);
   std::lock_guard<std::mutex> lock(ctx->mu);
+  if (ctx->prove_active) return fail(B200G16_ERR_STATE, "verify: a prove is open on this ctx (prove_begin_dev without _end_dev)");
   B200_CUDA(cudaSetDevice(ctx->device));
 
   // kSum = K[0] + sum_i pub_i K[i+1] (+ commitment): the library's own MSM on a scratch upload

@@ -180,21 +180,61 @@ def proof_write_to(ctx, proof, raw=False):
             + b"".join(e1[2 + i].tobytes() for i in range(k)) + e1[2 + k].tobytes())
 
 
-def proof_read_from(ctx, data, raw=False):
-    """(*Proof).ReadFrom -> Proof; raises ValueError on an invalid encoding (gnark returns the decoder's error)."""
-    s1, s2 = (64, 128) if raw else (32, 64)
-    o = 2 * s1 + s2
-    if len(data) < o + 4:
+class _PointReader:
+    """gnark-crypto's Decoder reads every point by its own flag bits: 0b00 = uncompressed record (64 / 128 bytes,
+    all zero = infinity), anything else = compressed record (32 / 64 bytes, 0b01 = infinity).  Records are
+    collected while the stream is walked and decoded in two GPU batches (compressed / uncompressed)."""
+
+    def __init__(self, data, what):
+        self.data, self.o, self.what, self.items = bytes(data), 0, what, []
+
+    def take(self, k):
+        if self.o + k > len(self.data):
+            raise ValueError(f"{self.what}: short buffer")
+        v = self.data[self.o:self.o + k]
+        self.o += k
+        return v
+
+    def u32(self):
+        return int.from_bytes(self.take(4), "big")
+
+    def point(self, group):
+        """Registers the next point; returns its index into the result of decode()."""
+        if self.o >= len(self.data):
+            raise ValueError(f"{self.what}: short buffer")
+        raw = (self.data[self.o] & 0xC0) == 0
+        size = (32 if group == 1 else 64) * (2 if raw else 1)
+        self.items.append((group, raw, self.take(size)))
+        return len(self.items) - 1
+
+    def decode(self, ctx):
+        out = [None] * len(self.items)
+        for group in (1, 2):
+            for raw in (False, True):
+                idx = [i for i, it in enumerate(self.items) if it[0] == group and it[1] == raw]
+                if not idx:
+                    continue
+                pts, ok = ctx.decode_points(b"".join(self.items[i][2] for i in idx), group=group, raw=raw)
+                if not ok.all():
+                    raise ValueError(f"{self.what}: invalid point encoding")
+                for j, i in enumerate(idx):
+                    out[i] = pts[j]
+        return out
+
+
+def proof_read_from(ctx, data, raw=None):
+    """(*Proof).ReadFrom -> Proof; raises ValueError on an invalid encoding (gnark returns the decoder's error).
+    Compressed and raw streams are both accepted (per-point flag bits, like gnark-crypto's Decoder); `raw` is
+    ignored and kept for the callers of the previous signature."""
+    rd = _PointReader(data, "groth16.Proof.ReadFrom")
+    ar, bs, krs = rd.point(1), rd.point(2), rd.point(1)
+    k = rd.u32()
+    if k > (len(rd.data) - rd.o) // 32:
         raise ValueError("groth16.Proof.ReadFrom: short buffer")
-    k = int.from_bytes(data[o:o + 4], "big")
-    if len(data) < o + 4 + (k + 1) * s1:
-        raise ValueError("groth16.Proof.ReadFrom: short buffer")
-    g1_bytes = data[:s1] + data[s1 + s2:o] + data[o + 4:o + 4 + (k + 1) * s1]
-    g1, ok1 = ctx.decode_points(g1_bytes, group=1, raw=raw)
-    g2, ok2 = ctx.decode_points(data[s1:s1 + s2], group=2, raw=raw)
-    if not (ok1.all() and ok2.all()):
-        raise ValueError("groth16.Proof.ReadFrom: invalid point encoding")
-    return Proof(g1[0], g1[1], g2[0], [g1[2 + i] for i in range(k)], g1[2 + k])
+    coms = [rd.point(1) for _ in range(k)]
+    pok = rd.point(1)
+    p = rd.decode(ctx)
+    return Proof(p[ar], p[krs], p[bs], [p[i] for i in coms], p[pok])
 
 
 def vk_write_to(ctx, vk, raw=False):
@@ -220,36 +260,28 @@ def vk_write_to(ctx, vk, raw=False):
     return out
 
 
-def vk_read_from(ctx, data, raw=False):
-    """(*VerifyingKey).ReadFrom -> VerifyingKey; raises ValueError on an invalid encoding."""
-    s1, s2 = (64, 128) if raw else (32, 64)
-    o = 0
-
-    def take(k):
-        nonlocal o
-        if o + k > len(data):
-            raise ValueError("groth16.VerifyingKey.ReadFrom: short buffer")
-        v = data[o:o + k]
-        o += k
-        return v
-    a1, b1, b2, g2, d1, d2 = take(s1), take(s1), take(s2), take(s2), take(s1), take(s2)
-    nk = int.from_bytes(take(4), "big")
-    kbytes = take(nk * s1)
+def vk_read_from(ctx, data, raw=None):
+    """(*VerifyingKey).ReadFrom -> VerifyingKey; raises ValueError on an invalid encoding.  Accepts compressed
+    and raw streams (per-point flag bits); `raw` is ignored."""
+    rd = _PointReader(data, "groth16.VerifyingKey.ReadFrom")
+    a1, b1, b2, g2, d1, d2 = rd.point(1), rd.point(1), rd.point(2), rd.point(2), rd.point(1), rd.point(2)
+    nk = rd.u32()
+    if nk > (len(rd.data) - rd.o) // 32:
+        raise ValueError("groth16.VerifyingKey.ReadFrom: short buffer")
+    ks = [rd.point(1) for _ in range(nk)]
     groups = []
-    for _ in range(int.from_bytes(take(4), "big")):
-        m = int.from_bytes(take(4), "big")
-        groups.append([int.from_bytes(take(8), "big") for _ in range(m)])
-    nck = int.from_bytes(take(4), "big")
+    for _ in range(rd.u32()):
+        m = rd.u32()
+        groups.append([int.from_bytes(rd.take(8), "big") for _ in range(m)])
+    nck = rd.u32()
     if nck > 1 or nck != len(groups):
         raise ValueError("groth16.VerifyingKey.ReadFrom: this backend supports at most one commitment")
-    ped = take(2 * s2) if nck else b""
-    p1, ok1 = ctx.decode_points(a1 + b1 + d1 + kbytes, group=1, raw=raw)
-    p2, ok2 = ctx.decode_points(b2 + g2 + d2 + ped, group=2, raw=raw)
-    if not (ok1.all() and ok2.all()):
-        raise ValueError("groth16.VerifyingKey.ReadFrom: invalid point encoding")
-    vk = VerifyingKey(p1[0], p1[3:3 + nk], p2[0], p2[1], p2[2], G1_Beta=p1[1], G1_Delta=p1[2])
+    ped = [rd.point(2), rd.point(2)] if nck else []
+    p = rd.decode(ctx)
+    vk = VerifyingKey(p[a1], np.stack([p[i] for i in ks]) if ks else np.zeros((0, 8), np.uint64), p[b2], p[g2], p[d2],
+                      G1_Beta=p[b1], G1_Delta=p[d1])
     if nck:
-        vk.PedersenG, vk.PedersenGSigmaNeg = p2[3], p2[4]
+        vk.PedersenG, vk.PedersenGSigmaNeg = p[ped[0]], p[ped[1]]
         vk.PublicAndCommitmentCommitted = groups[0]
         vk.has_commitment = True
     return vk
@@ -286,7 +318,7 @@ def commitment_challenge(commitment_limbs, public_committed_values):
     """gnark prove.go: hash_to_field("bsb22-commitment")(commitment.Marshal() || committed publics)."""
     c = np.asarray(commitment_limbs, dtype=np.uint64)
     if not c.any():
-        raw = bytes([0x40]) + bytes(63)
+        raw = bytes(64)             # Marshal() = RawBytes(): the uncompressed point at infinity is all zero on bn254
     else:
         raw = _fp_from(c[:4]).to_bytes(32, "big") + _fp_from(c[4:]).to_bytes(32, "big")
     msg = raw + b"".join(int(v % R_MOD).to_bytes(32, "big") for v in public_committed_values)

@@ -338,9 +338,13 @@ int b200g16_prove_h_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wi
 /* gnark-crypto ecc/bn254/marshal.go, applied element by element by the curve Encoder / Decoder to the
  * point slices of groth16_bn254.ProvingKey / VerifyingKey / Proof (gnark backend/groth16/bn254/
  * marshal.go WriteTo / WriteRawTo / ReadFrom).  Big-endian field elements, two flag bits on top of the
- * first byte: 0b00 uncompressed, 0b01 infinity, 0b10 / 0b11 compressed with the lexicographically
- * smallest / largest Y; G2 writes X.A1 before X.A0.  Fixed-size records: raw = 0 -> compressed
- * (G1 32 B, G2 64 B: G1Affine.Bytes / SetBytes), raw = 1 -> uncompressed (64 / 128 B: RawBytes).
+ * first byte: 0b00 uncompressed, 0b01 COMPRESSED infinity, 0b10 / 0b11 compressed with the
+ * lexicographically smallest / largest Y; G2 writes X.A1 before X.A0.  bn254 has two spare bits only, so
+ * the uncompressed point at infinity is flag 0b00 followed by zeros (an all-zero record).  Fixed-size
+ * records: raw = 0 -> compressed (G1 32 B, G2 64 B: G1Affine.Bytes / SetBytes; infinity = 0x40 then zeros),
+ * raw = 1 -> uncompressed (64 / 128 B: RawBytes; infinity = all zero; a 0x40 flag is invalid here because
+ * gnark's decoder would consume a compressed-size record for it — walk mixed streams record by record,
+ * as gnark_whir_b200/groth16.py _PointReader does).
  * decode: ok_out[i] = 1 for a valid encoding of a curve point (and, for G2 with subgroup_check, a
  * point of the r-torsion subgroup, as the Decoder checks by default); invalid records decode to
  * infinity with ok_out[i] = 0.  Reading a compressed key costs one square root per point, which is
@@ -355,7 +359,9 @@ int b200g16_g2_encode(b200g16_ctx* ctx, const uint64_t* points, size_t n, int ra
  * multi-GPU prove: sharded.prove_distributed).  begin: gathers + MSM B2, B1, A, K enqueued on the ctx's
  * streams, returns WITHOUT waiting.  end: MSM Z over d_h (N elements, bit-reversed), waits, assembles
  * the proof (or, for a partial pk, the five partial sums).  One prove in flight per ctx; d_wires must
- * stay valid until end returns; other calls on the ctx in between queue behind the MSMs. */
+ * stay valid until end returns.  Between begin and end the ctx accepts b200g16_ntt_dev,
+ * b200g16_h_pointwise_dev and b200g16_compute_h_dev (they queue behind the MSMs); every MSM, prove and
+ * verify entry point returns B200G16_ERR_STATE, because the pending MSMs own the result slots. */
 int b200g16_prove_begin_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_wires);
 int b200g16_prove_end_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_h, const uint64_t r[4],
                           const uint64_t s[4], b200g16_proof* proof_out);

@@ -78,7 +78,7 @@ def fr_hash(msg, dst, count=1):
 
 def g1_marshal(pt):
     if pt is None:
-        return bytes([0x40]) + bytes(63)
+        return bytes(64)            # G1Affine.Marshal() = RawBytes(): uncompressed infinity is all zero on bn254
     return pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
 
 

@@ -7,7 +7,9 @@ reached from the reference when a proof leaves the process (mt.go:496-497 keep i
 tooling serialises it).
 
 Point encodings (big-endian field elements, 2 flag bits in the most significant bits of the first byte):
-  0b00 uncompressed (X || Y)         0b01 point at infinity (rest zero; compressed or uncompressed length)
+  0b00 uncompressed (X || Y; the point at infinity is X = Y = 0, i.e. an all-zero record: bn254 has only two
+       spare bits, so there is no "uncompressed infinity" flag)
+  0b01 COMPRESSED point at infinity (rest zero, compressed length: a decoder consumes 32 / 64 bytes)
   0b10 compressed, Y is the lexicographically smallest root        0b11 compressed, Y the largest
 G1: X is 32 bytes.  G2: X = X.A1 || X.A0 (64 bytes), Y likewise; "largest" compares A1 first, then A0.
 Slices: uint32 big-endian length, then the elements.
@@ -75,7 +77,7 @@ def g1_bytes(pt):
 def g1_raw_bytes(pt):
     """G1Affine.RawBytes() / Marshal(): 64 bytes uncompressed"""
     if pt is None:
-        return bytes([M_INFINITY]) + bytes(63)
+        return bytes(64)
     return pt[0].to_bytes(32, "big") + pt[1].to_bytes(32, "big")
 
 
@@ -88,7 +90,11 @@ def g1_set_bytes(buf):
             raise ValueError("invalid infinity encoding")
         return None, n
     if flag == M_UNCOMPRESSED:
+        if len(buf) < 64:
+            raise ValueError("short buffer")
         x, y = int.from_bytes(buf[:32], "big"), int.from_bytes(buf[32:64], "big")
+        if x == 0 and y == 0:
+            return None, 64
         if x >= P or y >= P or not bn.g1_on_curve((x, y)):
             raise ValueError("invalid point")
         return (x, y), 64
@@ -115,7 +121,7 @@ def g2_bytes(pt):
 
 def g2_raw_bytes(pt):
     if pt is None:
-        return bytes([M_INFINITY]) + bytes(127)
+        return bytes(128)
     (x0, x1), (y0, y1) = pt
     return b"".join(v.to_bytes(32, "big") for v in (x1, x0, y1, y0))
 
@@ -127,7 +133,11 @@ def g2_set_bytes(buf, subgroup_check=True):
             raise ValueError("invalid infinity encoding")
         return None, 64
     if flag == M_UNCOMPRESSED:
+        if len(buf) < 128:
+            raise ValueError("short buffer")
         x1, x0, y1, y0 = (int.from_bytes(buf[32 * i:32 * i + 32], "big") for i in range(4))
+        if x0 == x1 == y0 == y1 == 0:
+            return None, 128
         pt = ((x0, x1), (y0, y1))
         if max(x0, x1, y0, y1) >= P or not bn.g2_on_curve(pt):
             raise ValueError("invalid point")

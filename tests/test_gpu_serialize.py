@@ -54,6 +54,13 @@ def test_decode_rejects_invalid_records(ctx):
     off = p[0].to_bytes(32, "big") + ((p[1] + 1) % bn.P).to_bytes(32, "big")
     _, ok = ctx.decode_points(ser.g1_raw_bytes(p) + off, group=1, raw=True)
     assert list(ok) == [True, False]
+    # raw infinity is the all-zero record (bn254 has no "uncompressed infinity" flag); the compressed-infinity flag
+    # is invalid inside a raw batch (gnark's decoder would consume only 32 bytes for it)
+    assert ser.g1_raw_bytes(None) == bytes(64) and ser.g2_raw_bytes(None) == bytes(128)
+    pts, ok = ctx.decode_points(bytes(64) + bytes([0x40]) + bytes(63), group=1, raw=True)
+    assert list(ok) == [True, False] and not pts.any()
+    pts, ok = ctx.decode_points(bytes(128) + bytes([0x40]) + bytes(127), group=2, raw=True)
+    assert list(ok) == [True, False] and not pts.any()
     # G2: a twist point outside the r-torsion subgroup passes without the subgroup check only
     x = (5, 1)
     while True:
@@ -80,7 +87,9 @@ def test_proof_wire_format_round_trip(ctx, raw, with_commitment):
                       [bn.g1_to_array([c])[0] for c in coms], bn.g1_to_array([pk])[0])
     data = g16.proof_write_to(ctx, proof, raw=raw)
     assert data == ser.proof_write(ar, bs, krs, coms, pk, raw=raw)               # byte-exact with the oracle
-    back = g16.proof_read_from(ctx, data, raw=raw)
+    back = g16.proof_read_from(ctx, data)               # per-point flag bits: no raw / compressed hint needed
+    if not with_commitment:                              # CommitmentPok = infinity: 0x40 record or 64 zero bytes
+        assert data.endswith(bytes(64) if raw else bytes([0x40]) + bytes(31))
     assert np.array_equal(back.Ar, proof.Ar) and np.array_equal(back.Bs, proof.Bs) and np.array_equal(back.Krs, proof.Krs)
     assert len(back.Commitments) == len(coms) and np.array_equal(back.CommitmentPok, proof.CommitmentPok)
     with pytest.raises(ValueError):

@@ -290,6 +290,14 @@ def test_point_encodings_round_trip_and_sign_rule():
     assert ser.g1_bytes(bn.G1_GEN) == bytes([0x80]) + bytes(30) + bytes([1])
     assert ser.g1_bytes(bn.g1_neg(bn.G1_GEN)) == bytes([0xC0]) + bytes(30) + bytes([1])
     assert ser.g1_bytes(None) == bytes([0x40]) + bytes(31) and ser.g1_set_bytes(ser.g1_bytes(None)) == (None, 32)
+    # bn254 has two flag bits: RawBytes() of infinity is the all-zero record, a 0x40 flag always means a
+    # compressed-size record (a reader positioned on it consumes 32 / 64 bytes, not 64 / 128)
+    assert ser.g1_raw_bytes(None) == bytes(64) and ser.g1_set_bytes(bytes(64)) == (None, 64)
+    assert ser.g2_raw_bytes(None) == bytes(128) and ser.g2_set_bytes(bytes(128)) == (None, 128)
+    assert ser.g1_set_bytes(bytes([0x40]) + bytes(63)) == (None, 32)
+    assert ser.g2_set_bytes(bytes([0x40]) + bytes(127)) == (None, 64)
+    raw_proof = ser.proof_write(bn.G1_GEN, bn.G2_GEN, bn.G1_GEN, [], None, raw=True)
+    assert len(raw_proof) == 64 + 128 + 64 + 4 + 64 and ser.proof_read(raw_proof)[4:] == (None, len(raw_proof))
     for _ in range(8):
         p1 = bn.g1_mul(bn.G1_GEN, rng.randrange(1, bn.R))
         p2 = bn.g2_mul(bn.G2_GEN, rng.randrange(1, bn.R))
