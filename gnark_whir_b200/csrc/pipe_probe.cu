@@ -177,7 +177,29 @@ __global__ void __launch_bounds__(128) k_fp52_probe(uint32_t* __restrict__ data,
 
 // variant: 0 = 1 DFMA chain, 1 = 2 DFMA chains, 2 = 4 DFMA chains, 3 = 1 integer + 1 DFMA chain,
 // 4 = 1 integer + 2 DFMA chains, 5 = 2 integer chains (reference point in the same harness)
+// The device's DFMA product against the host's exact emulation of the same source (fp52.cuh) and against the
+// integer multiplier's value of the same chain: thread 0 of a one-CTA launch, 64 dependent products.
+static int fp52_selfcheck(b200g16_ctx* ctx) {
+  const int iters = 64;
+  B200_TRY(ctx->io_a.ensure(128 * 32));
+  B200_CUDA(cudaMemsetAsync(ctx->io_a.p, 0x1a, 128 * 32, ctx->stream));
+  k_fp52_probe<0, 1><<<1, 128, 0, ctx->stream>>>(ctx->io_a.as<uint32_t>(), iters);
+  uint32_t got[8], w[8], want[8];
+  B200_CUDA(cudaMemcpyAsync(got, ctx->io_a.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 8; k++) w[k] = 0x1a1a1a1au & (k == 7 ? 0x0fffffffu : 0xffffffffu);
+  Fp52 y = Fp52::from_words(w);
+  w[0] ^= 1u;
+  Fp52 x = Fp52::from_words(w);
+  for (int it = 0; it < iters; it++) x = Fp52::mul(x, y);
+  x.to_words(want);
+  if (memcmp(got, want, 32) != 0)
+    return fail(B200G16_ERR_CUDA, "fp52_probe: the device's DFMA Montgomery product differs from the host emulation");
+  return 0;
+}
+
 int fp52_probe(b200g16_ctx* ctx, int variant, int blocks_per_sm, int iters, double* modmul_per_s, float* ms_out) {
+  B200_TRY(fp52_selfcheck(ctx));
   size_t threads = (size_t)ctx->sm_count * blocks_per_sm * 128;
   B200_TRY(ctx->io_a.ensure(threads * 32));
   B200_CUDA(cudaMemsetAsync(ctx->io_a.p, 0x1a, threads * 32, ctx->stream));

@@ -18,6 +18,11 @@ def _rand_points(rng, n):
     return ks, bn.g1_batch_mul_gen(ks)
 
 
+def test_fp52_probe_runs(ctx):
+    rate, ms = ctx.fp52_probe(1, blocks_per_sm=4, iters=200)
+    assert rate > 1e9 and ms > 0
+
+
 def test_modmul_probe_runs(ctx):
     rate, ms = ctx.modmul_probe(blocks_per_sm=4, chains=4, iters=500)
     assert rate > 1e9 and ms > 0

@@ -141,6 +141,36 @@ def test_device_montgomery_algorithm_pinned(fieldlib, rng):
     fieldlib.fr_inv(_limbs(a * (1 << 256) % R), o); assert _val(o) * rir % R == pow(a, -1, R)
 
 
+def test_fp64_pipe_montgomery_product_pinned(tmp_path, rng):
+    """fp52.cuh: the 5 x 52-bit DFMA.RZ Montgomery product (R' = 2^260), executed here through its exact 128-bit
+    emulation of fma.rz.f64 — the GPU runs the same source with the hardware instruction (b200g16_fp52_probe
+    compares the two on the device).  Lazy result: congruent to a b 2^-260 and below a b / 2^260 + M."""
+    src = tmp_path / "f52.cpp"
+    src.write_text('''
+#include <cstring>
+#include "fp52.cuh"
+using namespace b200;
+extern "C" {
+void fp52_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp52::mul(Fp52::from_words(a), Fp52::from_words(b)).to_words(r); }
+void fr52_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr52::mul(Fr52::from_words(a), Fr52::from_words(b)).to_words(r); }
+}
+''')
+    out = tmp_path / "f52.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                    "-I", os.path.join(ROOT, "gnark_whir_b200", "csrc"), str(src), "-o", str(out)], check=True)
+    L = ctypes.CDLL(str(out))
+    o = (ctypes.c_uint32 * 8)()
+    top = (1 << 52) - 1
+    for fn, m in ((L.fp52_mul, P), (L.fr52_mul, R)):
+        ri = pow(1 << 260, -1, m)
+        edge = [0, 1, m - 1, m, 2 * m, (1 << 256) - 1, top, top << 52, sum(top << (52 * k) for k in range(4)) | (0xffffffffffff << 208)]
+        cases = [(a, b) for a in edge for b in edge] + [(rng.randrange(1 << 256), rng.randrange(1 << 256)) for _ in range(3000)]
+        for a, b in cases:
+            fn(_limbs(a), _limbs(b), o)
+            v = _val(o)
+            assert v % m == a * b * ri % m and v <= (a * b >> 260) + m
+
+
 def test_host_mirror_layout_and_hash_agree_with_oracle(rng):
     vals = [0, 1, R - 1] + [rng.randrange(R) for _ in range(5)]
     assert np.array_equal(g16.fr_array(vals), bn.fr_to_mont_array(vals))
