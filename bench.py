@@ -435,6 +435,10 @@ def run_b200(args, rank, local_rank, world):
         partial = ctx.msm(bases, sc_pageable)
         return sharded.exchange_and_combine(partial, 1, device=dev)
 
+    sampler = ClockSampler(local_rank)     # nvidia-smi needs a moment to start: sample from the gate onwards
+    if rank == 0:
+        sampler.start()
+
     # ---- parity gate before timing: the COMBINED point (all ranks' shards) == closed form
     # [sum over ranks of <k, s>] G: per-rank dot products by the C oracle, gathered, added mod r, one scalar mul
     dots = D.gather_fr(cport.fr_dot(ks, sc_host, host_threads() if world == 1 else max(1, host_threads() // world)))
@@ -468,9 +472,6 @@ def run_b200(args, rank, local_rank, world):
         ms = D.reduce(e0.elapsed_time(e1) / steps, "max")
         return ms, phases, ctx.launch_count() - l0, res
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms, phases, launches, res_a = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _, _, res_b = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     clocks = sampler.stop() if rank == 0 else None

@@ -18,7 +18,8 @@
 //                 XYZZ adds (10 modmul) on the integer pipe; next point prefetched during the add
 //   ---- "tail", on a second stream under the next MSM's work above ----
 //   k_merge_pass  fan-in-4 tree over the partials of split buckets
-//   k_reduce, k_sum_pass  running-sum bucket reduction in chunks, then fan-in-4 plain sums per window
+//   k_reduce_first / _level / _weights, k_sum_pass  log-depth tree for sum_b (b+1) B_b (bit decomposition of the
+//                 weights: 2 additions per bucket in total, dependency depth c instead of a running-sum chain)
 //   host          Horner over the window sums + one inversion -> affine
 //
 // With a window table over the bases (b200g16_bases_precompute: row k = 2^(ck) P_i) all digits address
@@ -130,27 +131,55 @@ __global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partia
   partials[t] = acc;
 }
 
-// thread per (window, chunk): sum_{b in chunk} (b+1) * B_b via a running sum from the top
+// ---- bucket reduction  S_w = sum_b (b + 1) B_b  as a log-depth tree (no running sums, no serial chains).
+// With n = log2(#buckets):  S = G + sum_m 2^m U_m,  G = sum_b B_b,  U_m = sum of the buckets whose index has bit m
+// set.  All n + 1 sums come out of ONE in-place halving schedule over a dense array A of the bucket values:
+// level l (1..n) folds the main region A[0, 2^(n-l+1)) onto its lower half — the intact upper half is exactly the
+// set "bit n-l set" of the folded index and becomes region j = l at offset 2^(n-l) — and halves every older
+// region in place.  Before level l all l regions have 2^(n-l+1) items, so a level is l * 2^(n-l) independent
+// additions, 2 * 2^n in total (the running sum's count), and the dependency depth is n additions instead of
+// ~2 * chunk + 1.5 c.  Afterwards A[0] = G and A[2^m] = U_m; k_reduce_weights scales them by 2^m (m doublings,
+// one thread each) and the fan-in-4 sum passes below add the n + 1 terms.
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce(const XYZZ<F>* __restrict__ partials,
-                                                 const uint32_t* __restrict__ counts,
-                                                 const uint32_t* __restrict__ task_off, int W, uint32_t nbw,
-                                                 uint32_t ch, uint32_t nch, int cbits, XYZZ<F>* __restrict__ chunks) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (uint32_t)W * nch) return;
-  uint32_t w = g / nch, k = g % nch;
-  uint32_t lo = k * ch;
-  const uint32_t first = w * nbw + lo;  // bucket b's value = first partial of the bucket (after k_merge_pass)
-  XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-  for (uint32_t j = ch; j-- > 0;) {
-    if (counts[first + j]) running.add(partials[task_off[first + j]]);
-    acc.add(running);
-  }
-  if (lo) {
-    running.mul_small(lo, cbits);
-    acc.add(running);
-  }
-  chunks[g] = acc;
+__global__ void __launch_bounds__(128) k_reduce_first(const XYZZ<F>* __restrict__ partials,
+                                                       const uint32_t* __restrict__ counts,
+                                                       const uint32_t* __restrict__ task_off, uint32_t Wr, uint32_t nbw,
+                                                       XYZZ<F>* __restrict__ A) {
+  const uint32_t half = nbw >> 1;
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Wr * half) return;
+  const uint32_t w = g / half, i = g % half;
+  const uint32_t first = w * nbw;  // bucket b's value = first partial of the bucket (after k_merge_pass)
+  XYZZ<F> lo = counts[first + i] ? partials[task_off[first + i]] : XYZZ<F>::inf();
+  const XYZZ<F> hi = counts[first + i + half] ? partials[task_off[first + i + half]] : XYZZ<F>::inf();
+  A[first + i + half] = hi;
+  lo.add(hi);
+  A[first + i] = lo;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce_level(XYZZ<F>* __restrict__ A, uint32_t Wr, uint32_t nbw, uint32_t l) {
+  const uint32_t s = nbw >> l, per_w = l * s;
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Wr * per_w) return;
+  const uint32_t w = g / per_w, r = g % per_w, j = r / s, i = r % s;
+  XYZZ<F>* p = A + (size_t)w * nbw + (j ? (nbw >> j) : 0u) + i;
+  XYZZ<F> a = p[0];
+  a.add(p[s]);
+  p[0] = a;
+}
+
+// terms[w][m] = 2^m * U_m (m < n), terms[w][n] = G
+template <class F>
+__global__ void __launch_bounds__(32) k_reduce_weights(const XYZZ<F>* __restrict__ A, uint32_t Wr, uint32_t nbw, uint32_t n,
+                                                        XYZZ<F>* __restrict__ terms) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Wr * (n + 1)) return;
+  const uint32_t w = g / (n + 1), m = g % (n + 1);
+  XYZZ<F> v = A[(size_t)w * nbw + (m == n ? 0u : (1u << m))];
+  if (m < n)
+    for (uint32_t k = 0; k < m; k++) v.dbl();
+  terms[g] = v;
 }
 
 // plain sums, fan-in 4: out[w][g] = sum_{j<4} in[w][4 g + j]   (len_in items per window, thread per g);
@@ -204,11 +233,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   if ((double)n * cfg.W >= 4.0e9) return fail(B200G16_ERR_ARG, "msm: n*W overflows 32-bit entry index");
   size_t m_max = n * (size_t)cfg.W;
   cfg.target_tasks = (uint32_t)ctx->sm_count * 2048u;  // ~4 waves of 512 resident threads per SM
-  // buckets per reduce thread: the reduction is a serial chain of 2 ch + ~1.5 c group operations per
-  // thread, so small bucket sets (latency-bound) get short chunks, large ones amortise the lo * running
-  // multiplication over more buckets
-  cfg.ch = cfg.nbw < 8 ? cfg.nbw : (cfg.nb <= (1u << 19) ? 8 : 32);
-  cfg.nch = cfg.nbw / cfg.ch;
+  cfg.ch = 1;   // (unused since the tree reduction: one bucket per leaf)
+  cfg.nch = cfg.nbw;
   // #tasks = sum ceil(cnt/seg) <= nb + total/seg <= nb + target (k_pick_seg keeps seg >= total/target)
   size_t max_tasks = (size_t)cfg.nb + cfg.target_tasks + 64;
 
@@ -231,7 +257,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
     B200_TRY(ws.misc[q].ensure(scan_off + ((size_t)cfg.nb / 2048 + 4) * sizeof(uint2) + 2 * 4096 * sizeof(uint32_t)));
     B200_TRY(ws.tasks[q].ensure(2 * max_tasks * sizeof(uint32_t)));  // task_bucket, task_order
     B200_TRY(ws.partials[q].ensure(max_tasks * sizeof(XYZZ<F>)));
-    B200_TRY(ws.chunks[q].ensure(2 * (size_t)cfg.Wr * cfg.nch * sizeof(XYZZ<F>)));  // chunk sums + k_sum_pass ping-pong
+    // dense bucket array of the reduction tree + two ping-pong rows of c terms per window for the sum passes
+    B200_TRY(ws.chunks[q].ensure(((size_t)cfg.Wr * cfg.nbw + 2 * (size_t)cfg.Wr * (cfg.c + 1)) * sizeof(XYZZ<F>)));
   }
   const size_t slot_bytes = MSM_MAX_WINDOWS * sizeof(XYZZ<Fp2>);
   if (ws.pinned_cap < MSM_SLOTS * slot_bytes) {
@@ -294,13 +321,17 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
     k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, tail>>>(partials, task_bucket, counts, task_off, totals,
                                                              (uint32_t)stride);
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
-  k_reduce<F><<<cdiv((size_t)cfg.Wr * cfg.nch, 128), 128, 0, tail>>>(partials, counts, task_off, cfg.Wr, cfg.nbw, cfg.ch,
-                                                                      cfg.nch, cfg.c, chunks);
-  // chunk sums -> one sum per window: ping-pong between the two halves of the chunk buffer
-  XYZZ<F>* cur = chunks;
-  XYZZ<F>* nxt = chunks + (size_t)cfg.Wr * cfg.nch;
-  int sum_levels = 0;
-  for (uint32_t len = cfg.nch; len > 1; sum_levels++) {
+  const uint32_t nlev = (uint32_t)cfg.c - 1;  // log2(buckets per window)
+  k_reduce_first<F><<<cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128), 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr,
+                                                                                 cfg.nbw, chunks);
+  for (uint32_t l = 2; l <= nlev; l++)
+    k_reduce_level<F><<<cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), 128), 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+  // 2^m U_m and G -> nlev + 1 terms per window, then plain fan-in-4 sums: ping-pong between two rows behind the tree
+  XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;
+  XYZZ<F>* nxt = cur + (size_t)cfg.Wr * (nlev + 1);
+  k_reduce_weights<F><<<cdiv((size_t)cfg.Wr * (nlev + 1), 32), 32, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, nlev, cur);
+  int sum_levels = (int)nlev + 1;  // counted as launches below
+  for (uint32_t len = nlev + 1; len > 1; sum_levels++) {
     const uint32_t len_out = (len + SUM_FANIN - 1) / SUM_FANIN, total_out = (uint32_t)cfg.Wr * len_out;
     k_sum_pass<F><<<cdiv(total_out, 128), 128, 0, tail>>>(cur, len, len_out, total_out, nxt);
     XYZZ<F>* t = cur; cur = nxt; nxt = t;
@@ -308,7 +339,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   }
   windows = cur;  // Wr items
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
-  ctx->launches += 2 + merge_levels + sum_levels;
+  ctx->launches += merge_levels + sum_levels;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.Wr * sizeof(XYZZ<F>),
                             cudaMemcpyDeviceToHost, tail));

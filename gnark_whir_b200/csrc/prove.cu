@@ -15,33 +15,7 @@
 //   Ar  = A + alpha + r*delta
 //   Bs1 = B1 + beta + s*delta           Bs = B2 + beta2 + s*delta2
 //   Krs = K + Z + (-rs)*delta + s*Ar + r*Bs1
-#include "msm_impl.cuh"
-
-namespace b200 {
-int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time);
-// instantiated in msm_g1.cu / msm_g2.cu
-extern template int msm_enqueue<Fp>(b200g16_ctx*, const Affine<Fp>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
-extern template int msm_collect<Fp>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp>*);
-extern template int msm_enqueue<Fp2>(b200g16_ctx*, const Affine<Fp2>*, const MsmTable*, const Fr*, size_t, int, MsmCfg*, bool, bool);
-extern template int msm_collect<Fp2>(b200g16_ctx*, int, const MsmCfg&, Affine<Fp2>*);
-}  // namespace b200
-
-struct b200g16_pk {
-  int device = 0;
-  unsigned log2n = 0;
-  size_t n_wires = 0;
-  // resident point vectors; owned[i] tells whether pk_free releases them
-  b200g16_bases* vec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // A, B1, K, Z, B2
-  bool owned[5] = {false, false, false, false, false};
-  b200::G1Affine alpha, beta, delta;
-  b200::G2Affine beta2, delta2;
-  // wire -> scalar-vector gather lists (device): A, B, K
-  uint32_t* d_idx[3] = {nullptr, nullptr, nullptr};
-  size_t n_idx[3] = {0, 0, 0};
-  size_t off_z = 0;     // this ctx holds Z[off_z, off_z + n_z)
-  size_t n_z = 0;
-  bool partial = false; // shard of a key: prove returns partial MSM sums only
-};
+#include "prove.cuh"
 
 namespace b200 {
 
@@ -69,6 +43,15 @@ static Affine<F> host_scalar_mul_aff(const Affine<F>& p, const Fr& k_mont) {
 }
 
 template <class F>
+Affine<F> host_sum_points(const Affine<F>* pts, int n) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int i = 0; i < n; i++) acc.madd(pts[i]);
+  return acc.to_affine();
+}
+template Affine<Fp> host_sum_points<Fp>(const Affine<Fp>*, int);
+template Affine<Fp2> host_sum_points<Fp2>(const Affine<Fp2>*, int);
+
+template <class F>
 static Affine<F> host_sum(std::initializer_list<Affine<F>> pts) {
   XYZZ<F> acc = XYZZ<F>::inf();
   for (const auto& p : pts) acc.madd(p);
@@ -90,7 +73,7 @@ static int build_index(const uint8_t* skip, size_t n_wires, size_t off, size_t e
   return 0;
 }
 
-static void pk_release(b200g16_pk* pk) {
+void pk_release(b200g16_pk* pk) {
   if (!pk) return;
   cudaSetDevice(pk->device);
   for (int i = 0; i < 5; i++)
@@ -100,7 +83,7 @@ static void pk_release(b200g16_pk* pk) {
   delete pk;
 }
 
-static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out) {
+int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out) {
   if (!ctx || !d || !out) return fail(B200G16_ERR_ARG, "pk_upload: null");
   if (!d->g1_alpha || !d->g1_beta || !d->g1_delta || !d->g2_beta || !d->g2_delta)
     return fail(B200G16_ERR_ARG, "pk_upload: alpha/beta/delta missing");
@@ -161,14 +144,9 @@ static int pk_build(b200g16_ctx* ctx, const b200g16_pk_desc* d, b200g16_pk** out
   return 0;
 }
 
-// The multiples of delta do not depend on any MSM result: prove_device computes them on the host
-// while the GPU is still working.
-struct DeltaMultiples {
-  G1Affine r_delta, s_delta, kr_delta;  // r*delta, s*delta, (-rs)*delta
-  G2Affine s_delta2;                    // s*delta2
-};
-
-static DeltaMultiples delta_multiples(const b200g16_pk* pk, const Fr& r, const Fr& s) {
+// The multiples of delta do not depend on any MSM result: the prove computes them on the host while the GPU
+// is still working.
+DeltaMultiples delta_multiples(const b200g16_pk* pk, const Fr& r, const Fr& s) {
   DeltaMultiples m;
   m.r_delta = host_scalar_mul_aff<Fp>(pk->delta, r);
   m.s_delta = host_scalar_mul_aff<Fp>(pk->delta, s);
@@ -178,9 +156,9 @@ static DeltaMultiples delta_multiples(const b200g16_pk* pk, const Fr& r, const F
 }
 
 // Ar, Bs, Krs (and bs1) from the five complete MSM results.
-static void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, const G1Affine& A, const G1Affine& B1,
-                              const G1Affine& K, const G1Affine& Z, const G2Affine& B2, const Fr& r, const Fr& s,
-                              b200g16_proof* out) {
+void prove_finish_host(const b200g16_pk* pk, const DeltaMultiples& dm, const G1Affine& A, const G1Affine& B1,
+                       const G1Affine& K, const G1Affine& Z, const G2Affine& B2, const Fr& r, const Fr& s,
+                       b200g16_proof* out) {
   G1Affine ar = host_sum<Fp>({A, pk->alpha, dm.r_delta});
   G1Affine bs1 = host_sum<Fp>({B1, pk->beta, dm.s_delta});
   G1Affine krs = host_sum<Fp>({K, Z, dm.kr_delta, host_scalar_mul_aff<Fp>(ar, s), host_scalar_mul_aff<Fp>(bs1, r)});
@@ -207,7 +185,7 @@ static int prove_enqueue_one(b200g16_ctx* ctx, const b200g16_pk* pk, int i, cons
 
 // Gathers + the four MSMs over witness values — G2 leading: its bucket reduction is the longest tail and
 // hides behind the G1 MSMs that follow.  Enqueues only; no synchronisation.
-static int prove_front(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, int* ev_io) {
+int prove_front(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires, int* ev_io) {
   if (ctx->prove_active) return fail(B200G16_ERR_STATE, "prove: another prove is already open on this ctx");
   cudaStream_t st = ctx->stream;
   int ev = *ev_io;
@@ -237,8 +215,8 @@ static int prove_front(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_wires
 }
 
 // d_h: h (N elements, bit-reversed).  Z MSM, join, host assembly.
-static int prove_back(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_h, const Fr& r, const Fr& s,
-                      b200g16_proof* out, int* ev_io) {
+int prove_back(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_h, const Fr& r, const Fr& s,
+               b200g16_proof* out, int* ev_io) {
   if (!ctx->prove_active || ctx->prove_pk != pk) return fail(B200G16_ERR_STATE, "prove: no matching prove_begin on this ctx");
   ctx->prove_active = false;
   cudaStream_t st = ctx->stream;

@@ -80,6 +80,21 @@ SIGNATURES = {
     "b200g16_g2_decode": (C.c_int, [_vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp]),
     "b200g16_g1_encode": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp]),
     "b200g16_g2_encode": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp]),
+    "b200g16_group_init": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
+    "b200g16_group_destroy": (None, [_vp]),
+    "b200g16_group_size": (C.c_int, [_vp]),
+    "b200g16_group_ctx": (_vp, [_vp, C.c_int]),
+    "b200g16_host_register": (C.c_int, [_vp, _sz]),
+    "b200g16_host_unregister": (C.c_int, [_vp]),
+    "b200g16_group_bases_upload_g1": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_group_bases_upload_g2": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200g16_group_bases_precompute": (C.c_int, [_vp, _vp, C.c_int]),
+    "b200g16_group_bases_free": (None, [_vp]),
+    "b200g16_group_msm_g1": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "b200g16_group_msm_g2": (C.c_int, [_vp, _vp, _vp, _sz, _vp]),
+    "b200g16_group_pk_upload": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "b200g16_group_pk_free": (None, [_vp]),
+    "b200g16_group_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -174,6 +189,127 @@ class ProofOut(C.Structure):
 
     def as_dict(self):
         return {name: np.array(getattr(self, name)[:], dtype=np.uint64) for name, _ in self._fields_}
+
+
+def _pk_desc(log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2, infinity_a, infinity_b, k_skip,
+             partial=False, offsets=(0, 0, 0, 0), precompute=False):
+    """struct b200g16_pk_desc from numpy arrays / Bases handles -> (desc, buffers to keep alive during the call)"""
+    keep = []
+
+    def vec(v, cols):
+        if isinstance(v, Bases):
+            return None, v.handle, v.n
+        a = _u64(v, cols)
+        keep.append(a)
+        return _ptr(a), None, a.shape[0]
+
+    d = PkDesc()
+    d.log2_domain, d.n_wires = log2_domain, n_wires
+    d.partial = int(bool(partial))
+    d.precompute = int(bool(precompute))
+    d.off_a, d.off_b, d.off_k, d.off_z = [int(x) for x in offsets]
+    d.g1_a, d.res_a, d.n_a = vec(A, 8)
+    d.g1_b, d.res_b, d.n_b = vec(B, 8)
+    d.g1_k, d.res_k, d.n_k = vec(K, 8)
+    d.g1_z, d.res_z, d.n_z = vec(Z, 8)
+    d.g2_b, d.res_b2, nb2 = vec(B2, 16)
+    if nb2 != d.n_b:
+        raise B200Error("pk_upload: len(G2.B) != len(G1.B)")
+    for name, val, w in (("g1_alpha", alpha, 8), ("g1_beta", beta, 8), ("g1_delta", delta, 8),
+                         ("g2_beta", beta2, 16), ("g2_delta", delta2, 16)):
+        a = _u64(val).reshape(w)
+        keep.append(a)
+        setattr(d, name, _ptr(a))
+    for name, val in (("infinity_a", infinity_a), ("infinity_b", infinity_b), ("k_skip", k_skip)):
+        a = np.ascontiguousarray(val, dtype=np.uint8)
+        if a.shape[0] != n_wires:
+            raise B200Error(f"pk_upload: {name} must have n_wires entries")
+        keep.append(a)
+        setattr(d, name, _ptr(a))
+    return d, keep
+
+
+def host_register(arr):
+    """Page-lock a numpy array in place (b200g16_host_register); returns the array."""
+    _check(load().b200g16_host_register(_ptr(arr), arr.nbytes))
+    return arr
+
+
+def host_unregister(arr):
+    _check(load().b200g16_host_unregister(_ptr(arr)))
+
+
+class Group:
+    """Several GPUs driven from this one process (b200g16_group_*): point-range shards of the proving key, peer
+    copies for h, partial points added on the host.  devices may repeat a device (several shards on one GPU)."""
+
+    def __init__(self, devices):
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = _vp()
+        _check(load().b200g16_group_init(arr, len(devices), C.byref(h)))
+        self.h, self.devices = h, list(devices)
+
+    def close(self):
+        if self.h:
+            load().b200g16_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __len__(self):
+        return int(load().b200g16_group_size(self.h))
+
+    def ctx(self, i):
+        """Borrowed Context of the i-th device (do not close it)."""
+        c = Context.__new__(Context)
+        c.h, c.device = _vp(load().b200g16_group_ctx(self.h, i)), self.devices[i]
+        return c
+
+    def upload(self, points, group=1, precompute=False):
+        pts = _u64(points, 8 if group == 1 else 16)
+        h = _vp()
+        fn = load().b200g16_group_bases_upload_g1 if group == 1 else load().b200g16_group_bases_upload_g2
+        _check(fn(self.h, _ptr(pts), pts.shape[0], C.byref(h)))
+        if precompute:
+            _check(load().b200g16_group_bases_precompute(self.h, h, 0))
+        return (h, group, pts.shape[0])
+
+    def bases_free(self, gb):
+        load().b200g16_group_bases_free(gb[0])
+
+    def msm(self, gb, scalars):
+        h, group, n = gb
+        sc = _u64(scalars, 4)
+        out = np.zeros(8 if group == 1 else 16, dtype=np.uint64)
+        fn = load().b200g16_group_msm_g1 if group == 1 else load().b200g16_group_msm_g2
+        _check(fn(self.h, h, _ptr(sc), sc.shape[0], _ptr(out)))
+        return out
+
+    def pk_upload(self, log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2, infinity_a, infinity_b,
+                  k_skip, precompute=False):
+        """The whole key as host arrays; the library cuts and uploads the shards."""
+        d, keep = _pk_desc(log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2, infinity_a, infinity_b,
+                           k_skip, False, (0, 0, 0, 0), precompute)
+        h = _vp()
+        _check(load().b200g16_group_pk_upload(self.h, C.byref(d), C.byref(h)))
+        del keep
+        return h
+
+    def pk_free(self, pk):
+        load().b200g16_group_pk_free(pk)
+
+    def prove(self, pk, wires, a, b, c, r, s, want_h=False, log2_domain=None):
+        wires, a, b, c = _u64(wires, 4), _u64(a, 4), _u64(b, 4), _u64(c, 4)
+        r, s = _u64(r).reshape(4), _u64(s).reshape(4)
+        out = ProofOut()
+        h = np.zeros((1 << log2_domain, 4), dtype=np.uint64) if want_h else None
+        _check(load().b200g16_group_prove(self.h, pk, _ptr(wires), wires.shape[0], _ptr(a), _ptr(b), _ptr(c), a.shape[0],
+                                          _ptr(r), _ptr(s), C.byref(out), _ptr(h) if want_h else None))
+        return out.as_dict(), h
 
 
 class Bases:
@@ -348,40 +484,11 @@ class Context:
         """A/B/K/Z/B2: numpy point arrays (host) or Bases (already resident, borrowed).
         partial=True: the vectors are entries [off, off+len) of the full key vectors
         (offsets = (off_a, off_b, off_k, off_z)); prove() then returns partial MSM sums."""
-        keep = []                      # keep numpy buffers alive for the duration of the call
-
-        def vec(v, cols):
-            if isinstance(v, Bases):
-                return None, v.handle, v.n
-            a = _u64(v, cols)
-            keep.append(a)
-            return _ptr(a), None, a.shape[0]
-
-        d = PkDesc()
-        d.log2_domain, d.n_wires = log2_domain, n_wires
-        d.partial = int(bool(partial))
-        d.precompute = int(bool(precompute))
-        d.off_a, d.off_b, d.off_k, d.off_z = [int(x) for x in offsets]
-        d.g1_a, d.res_a, d.n_a = vec(A, 8)
-        d.g1_b, d.res_b, d.n_b = vec(B, 8)
-        d.g1_k, d.res_k, d.n_k = vec(K, 8)
-        d.g1_z, d.res_z, d.n_z = vec(Z, 8)
-        d.g2_b, d.res_b2, nb2 = vec(B2, 16)
-        if nb2 != d.n_b:
-            raise B200Error("pk_upload: len(G2.B) != len(G1.B)")
-        for name, val, w in (("g1_alpha", alpha, 8), ("g1_beta", beta, 8), ("g1_delta", delta, 8),
-                             ("g2_beta", beta2, 16), ("g2_delta", delta2, 16)):
-            a = _u64(val).reshape(w)
-            keep.append(a)
-            setattr(d, name, _ptr(a))
-        for name, val in (("infinity_a", infinity_a), ("infinity_b", infinity_b), ("k_skip", k_skip)):
-            a = np.ascontiguousarray(val, dtype=np.uint8)
-            if a.shape[0] != n_wires:
-                raise B200Error(f"pk_upload: {name} must have n_wires entries")
-            keep.append(a)
-            setattr(d, name, _ptr(a))
+        d, keep = _pk_desc(log2_domain, n_wires, A, B, K, Z, B2, alpha, beta, delta, beta2, delta2, infinity_a, infinity_b,
+                           k_skip, partial, offsets, precompute)
         h = _vp()
         _check(load().b200g16_pk_upload(self.h, C.byref(d), C.byref(h)))
+        del keep
         return h
 
     def pk_free(self, pk):

@@ -366,6 +366,51 @@ int b200g16_prove_begin_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* 
 int b200g16_prove_end_dev(b200g16_ctx* ctx, const b200g16_pk* pk, const void* d_h, const uint64_t r[4],
                           const uint64_t s[4], b200g16_proof* proof_out);
 
+/* ---- one process, several GPUs -------------------------------------------------------------------
+ * gnark's prover is ONE process calling groth16.Prove once (/root/reference/mt.go:496); a group lets that
+ * process spread the prove over the GPUs of a box without NCCL or helper processes.  A group owns one ctx per
+ * device (peer access enabled where the hardware offers it) and drives them with one host thread per device.
+ * Sharding is by point range (BASELINE.json north_star): device i holds entries [lo_i, hi_i) of every
+ * proving-key vector, lo/hi balanced to within one point.  devices[] may name a device more than once
+ * (several shards on one GPU: how the sharding logic is tested on a single-GPU box). */
+typedef struct b200g16_group b200g16_group;
+typedef struct b200g16_group_bases b200g16_group_bases;
+typedef struct b200g16_group_pk b200g16_group_pk;
+int b200g16_group_init(const int* devices, int n, b200g16_group** out);
+void b200g16_group_destroy(b200g16_group* g);
+int b200g16_group_size(const b200g16_group* g);
+/* The i-th device's context (owned by the group), for single-device calls in between. */
+b200g16_ctx* b200g16_group_ctx(b200g16_group* g, int i);
+
+/* Page-lock caller memory in place (cudaHostRegister, portable): Go slices are pageable, and H2D copies from
+ * pageable memory run at a fraction of PCIe speed (bench.py e2e_pageable).  Register the witness / a / b / c
+ * buffers once, reuse them across proves, unregister before the slice is freed or moved. */
+int b200g16_host_register(void* p, size_t bytes);
+int b200g16_host_unregister(void* p);
+
+/* Point vectors sharded over the group's devices, and MultiExp over them: each device receives its slice of
+ * the scalars and runs a local Pippenger; the n partial points are added on the host (n - 1 additions).
+ * n must equal the length the bases were uploaded with. */
+int b200g16_group_bases_upload_g1(b200g16_group* g, const uint64_t* points, size_t n, b200g16_group_bases** out);
+int b200g16_group_bases_upload_g2(b200g16_group* g, const uint64_t* points, size_t n, b200g16_group_bases** out);
+int b200g16_group_bases_precompute(b200g16_group* g, b200g16_group_bases* b, int window_bits);
+void b200g16_group_bases_free(b200g16_group_bases* b);
+int b200g16_group_msm_g1(b200g16_group* g, const b200g16_group_bases* b, const uint64_t* scalars, size_t n, uint64_t out[8]);
+int b200g16_group_msm_g2(b200g16_group* g, const b200g16_group_bases* b, const uint64_t* scalars, size_t n, uint64_t out[16]);
+
+/* The whole proving key (host arrays, desc->partial = 0, no res_* vectors) cut into point-range shards, one
+ * per device, uploaded (and given window tables when desc->precompute) in parallel. */
+int b200g16_group_pk_upload(b200g16_group* g, const b200g16_pk_desc* desc, b200g16_group_pk** out);
+void b200g16_group_pk_free(b200g16_group_pk* pk);
+/* b200g16_prove over the group: same arguments, same result (bit-identical to the single-GPU prove).
+ * a, b, c are uploaded to up to three devices (one vector each: iNTT + coset NTT there), the root device
+ * receives the other two by peer copies, finishes h and every device fetches its slice of h by one peer copy
+ * (cudaMemcpyPeerAsync over NVLink); the five MSMs run on every device's shard and the n x 5 partial points
+ * are added on the host. */
+int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* pk, const uint64_t* wires, size_t n_wires,
+                        const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
+                        const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out, uint64_t* h_out);
+
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);

@@ -22,11 +22,27 @@ int main(void) {
   if (out[0] == g[0] && out[1] == g[1]) return 13; /* doubling must move the point */
   b200g16_ctx* ctx = NULL;
   int st = b200g16_init(0, &ctx);
-  if (st == 0) { /* a GPU is present: fine, just tear down */
+  /* one-process multi-GPU surface: argument checks answer without a device, a group refuses to start without one */
+  b200g16_group* grp = NULL;
+  int devs[2] = {0, 0};
+  if (b200g16_group_init(NULL, 1, &grp) != B200G16_ERR_ARG) return 16;
+  if (b200g16_group_init(devs, 0, &grp) != B200G16_ERR_ARG) return 17;
+  if (b200g16_group_size(NULL) != 0 || b200g16_group_ctx(NULL, 0) != NULL) return 18;
+  if (b200g16_host_register(NULL, 0) != B200G16_ERR_ARG || b200g16_host_unregister(NULL) != B200G16_ERR_ARG) return 19;
+  if (b200g16_group_msm_g1(NULL, NULL, NULL, 0, out) != B200G16_ERR_ARG) return 20;
+  if (b200g16_group_pk_upload(NULL, &d, NULL) != B200G16_ERR_ARG) return 21;
+  if (b200g16_group_prove(NULL, NULL, NULL, 0, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL) != B200G16_ERR_ARG) return 22;
+  b200g16_group_bases_free(NULL);
+  b200g16_group_pk_free(NULL);
+  b200g16_group_destroy(NULL);
+  if (st == 0) { /* a GPU is present: a two-shard group on device 0 comes up and goes away */
     b200g16_destroy(ctx);
+    if (b200g16_group_init(devs, 2, &grp) != 0 || b200g16_group_size(grp) != 2 || !b200g16_group_ctx(grp, 1)) return 23;
+    b200g16_group_destroy(grp);
     printf("gpu\n");
     return 0;
   }
+  if (b200g16_group_init(devs, 2, &grp) == 0) return 24;
   if (st != B200G16_ERR_NO_DEVICE && st != B200G16_ERR_CUDA) return 14;
   if (strlen(b200g16_last_error()) == 0) return 15;
   printf("nogpu: %s\n", b200g16_last_error());
