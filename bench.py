@@ -292,8 +292,10 @@ def prove_bench(ctx, D, rank, L, args, steps, warmup, want_e2e, want_cpu):
     d_com = to_dev(torch, dev, committed[c_lo:c_hi])
     distributed_h = world > 1 and not args.replicated_h
 
+    xch1, xch48 = sharded.PointExchange(8, device=dev), sharded.PointExchange(48, device=dev)
+
     def gather_sum(points, group=1):
-        return sharded.exchange_and_combine(points, group, device=dev) if world > 1 else points
+        return xch1.combine(points, group) if world > 1 else points
 
     def step():
         com = gather_sum(ctx.msm(ped[0], d_com.data_ptr(), n=c_hi - c_lo))                     # Commit (inside Solve)
@@ -307,10 +309,7 @@ def prove_bench(ctx, D, rank, L, args, steps, warmup, want_e2e, want_cpu):
                 part = ctx.prove_h_dev(key.handle, d_w.data_ptr(), aa.data_ptr(), rr, ss)
             else:
                 part = ctx.prove_dev(key.handle, d_w.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
-            t = torch.from_numpy(sharded.pack_partials(part).view(np.int64).copy()).to(dev)
-            outs = [torch.empty_like(t) for _ in range(world)]
-            D.dist.all_gather(outs, t)
-            sums = sharded.sum_partials([o.cpu().numpy().view(np.uint64) for o in outs])
+            sums = sharded.sum_partials(list(xch48.gather(sharded.pack_partials(part))))
             proof = ctx.prove_finish(key.handle, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], rr, ss)
         pok = gather_sum(ctx.msm(ped[1], d_com.data_ptr(), n=c_hi - c_lo))                     # ProveKnowledge
         return proof, com, pok, aa
@@ -423,17 +422,16 @@ def run_b200(args, rank, local_rank, world):
     sc_pageable = sc_host.copy()
     sc_dev = sc_host_t.to(dev)
 
+    xch = sharded.PointExchange(8, device=dev)         # one G1 point per rank; buffers allocated once
+
     def step_resident():
-        partial = ctx.msm(bases, sc_dev.data_ptr(), n=m)
-        return sharded.exchange_and_combine(partial, 1, device=dev)
+        return xch.combine(ctx.msm(bases, sc_dev.data_ptr(), n=m), 1)
 
     def step_e2e():
-        partial = ctx.msm(bases, sc_host)              # H2D of this step's scalars happens inside
-        return sharded.exchange_and_combine(partial, 1, device=dev)
+        return xch.combine(ctx.msm(bases, sc_host), 1)     # H2D of this step's scalars happens inside
 
     def step_pageable():
-        partial = ctx.msm(bases, sc_pageable)
-        return sharded.exchange_and_combine(partial, 1, device=dev)
+        return xch.combine(ctx.msm(bases, sc_pageable), 1)
 
     sampler = ClockSampler(local_rank)     # nvidia-smi needs a moment to start: sample from the gate onwards
     if rank == 0:

@@ -65,8 +65,8 @@ static int fixed_base_entry(b200g16_ctx* ctx, const uint64_t* base, const uint64
 // Host scalars of a large MSM are uploaded in MSM_PIPE_CHUNKS pieces on a copy stream; piece j's
 // sub-MSM (its own point sub-range, its own result slot) runs while piece j+1 is still crossing PCIe,
 // and the host adds the partial results.  Below MSM_PIPE_MIN points one copy + one MSM is faster.
-constexpr size_t MSM_PIPE_MIN = (size_t)1 << 22;
-constexpr int MSM_PIPE_CHUNKS = 4;
+constexpr size_t MSM_PIPE_MIN = (size_t)1 << 20;
+constexpr int MSM_PIPE_CHUNKS = 4;   // at n >= 2^22; two pieces below (every sub-MSM pays its own sort and tail)
 
 template <class F>
 static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, size_t offset, const void* scalars,
@@ -89,9 +89,10 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     Fr* d = ctx->msm.scalars.as<Fr>();
     MsmCfg cfg[MSM_PIPE_CHUNKS];
     size_t lo[MSM_PIPE_CHUNKS + 1];
-    for (int j = 0; j <= MSM_PIPE_CHUNKS; j++) lo[j] = n * (size_t)j / MSM_PIPE_CHUNKS;
+    const int pieces = n >= ((size_t)1 << 22) ? MSM_PIPE_CHUNKS : 2;
+    for (int j = 0; j <= pieces; j++) lo[j] = n * (size_t)j / pieces;
     ctx->timings.n = 0;
-    for (int j = 0; j < MSM_PIPE_CHUNKS; j++) {
+    for (int j = 0; j < pieces; j++) {
       const size_t m = lo[j + 1] - lo[j];
       B200_CUDA(cudaMemcpyAsync(d + lo[j], h + lo[j], m * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
       B200_CUDA(cudaEventRecord(ctx->ev_copy[j], ctx->copy_stream));
@@ -102,7 +103,7 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     B200_TRY(msm_join(ctx));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (int j = 0; j < MSM_PIPE_CHUNKS; j++) {
+    for (int j = 0; j < pieces; j++) {
       Affine<F> part;
       B200_TRY(msm_collect<F>(ctx, j, cfg[j], &part));
       acc.madd(part);
@@ -243,7 +244,7 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->tail_stream);
   std::vector<DevBuf*> bufs = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->ntt.a, &ctx->ntt.b,
-                               &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->io_a,  &ctx->io_b,
+                               &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->ntt.fused, &ctx->io_a,  &ctx->io_b,
                                &ctx->io_c};
   for (int i = 0; i < MSM_SETS; i++)
     for (DevBuf* b : {&ctx->msm.counts[i], &ctx->msm.partials[i], &ctx->msm.chunks[i], &ctx->msm.misc[i], &ctx->msm.tasks[i]})

@@ -75,9 +75,10 @@ struct MsmWorkspace {
 };
 
 struct NttWorkspace {
-  DevBuf a, b, c, tw, coset;
+  DevBuf a, b, c, tw, coset, fused;
   int tw_log = -1;     // twiddle table covers 2^tw_log
   int coset_log = -1;  // coset tables built for exactly 2^coset_log
+  int fused_log = -1;  // computeH's fused scaling tables (g^i / N with and without 1 / (g^N - 1))
 };
 
 // descriptor of a window table attached to a bases vector (b200g16_bases_precompute)

@@ -313,8 +313,9 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
         B200_CUDA(cudaMemcpyAsync(bufs[v]->p, src[v], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, stm));
         if (N > n_constraints)
           B200_CUDA(cudaMemsetAsync((char*)bufs[v]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), stm));
-        B200_TRY(ntt_device(ctx, bufs[v]->as<Fr>(), L, 1, true, false, B200G16_DIF));
-        B200_TRY(ntt_device(ctx, bufs[v]->as<Fr>(), L, 1, false, true, B200G16_DIT));
+        Fr* one[1] = {bufs[v]->as<Fr>()};
+        const bool den[1] = {v != 1};   // (a b - c) / (g^N - 1) = (a / d) b - c / d: a and c carry the denominator
+        B200_TRY(ntt_coset_pair_device(ctx, one, 1, L, den));
         B200_CUDA(cudaEventRecord(g->ev_vec[v], stm));
         vec_ready[v].signal(0);
       }
@@ -329,7 +330,7 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
           DevBuf* rb[3] = {&g->ctx[o]->ntt.a, &g->ctx[o]->ntt.b, &g->ctx[o]->ntt.c};
           B200_CUDA(cudaMemcpyPeerAsync(bufs[v]->p, ctx->device, rb[v]->p, g->ctx[o]->device, N * sizeof(Fr), stm));
         }
-        B200_TRY(h_pointwise_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), L));
+        B200_TRY(h_pointwise_plain_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), L));
         B200_TRY(ntt_device(ctx, ctx->ntt.a.as<Fr>(), L, 1, true, true, B200G16_DIF));
         B200_CUDA(cudaEventRecord(g->ev_h, stm));
         h_ready.signal(0);

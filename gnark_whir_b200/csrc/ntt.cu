@@ -83,6 +83,7 @@ struct NttPassArgs {
   const Fr* tw;
   const Fr* pre;    // multiply on load by pre[idx]  (nullptr = none)
   const Fr* post;   // multiply on store by post[idx] (nullptr = none)
+  const Fr* post_vec[3];  // post_mode == 2 with nvecs > 0: per-vector tables (computeH's fused scalings)
   Fr post_const;    // used when post_mode == 1
   uint32_t tw_half;
   int tw_sh;
@@ -92,6 +93,11 @@ struct NttPassArgs {
   int inverse;
 };
 
+// One pass = k radix-2 levels over the index bits [b0, b0 + k) of a tile of 2^k rows x 2^logc columns.  The FIRST
+// level reads its operands straight from global memory (scaled by the coset table when the pass carries one) and
+// the LAST level stores its results straight to global memory (scaled by 1/N or a table): the tile makes k - 1
+// round trips through shared memory instead of k + 1, with k - 1 barriers instead of k + 1, and the global loads
+// of one warp overlap the butterflies of the others instead of forming a phase of their own.
 // TFAST: rows contiguous in memory (b0 == 0) -> row index fastest in shared memory.
 template <bool DIT, bool TFAST>
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
@@ -103,23 +109,11 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
   const uint32_t lowmask = (1u << b0) - 1u;
   const uint32_t tile = blockIdx.x;
   Fr* data = A.nvecs ? A.vecs[blockIdx.y] : A.data + (size_t)blockIdx.y * ((size_t)1 << L);  // batched transforms
+  const Fr* post = (A.post_mode == 2 && A.nvecs) ? A.post_vec[blockIdx.y] : A.post;
 
-  // ---- load
-  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
-    uint32_t t, c;
-    if (TFAST) { t = x & (rows - 1); c = x >> k; }
-    else { c = x & ((1u << logc) - 1); t = x >> logc; }
-    uint32_t u = (tile << logc) + c;
-    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
-    Fr v = ld_fr(data + i);
-    if (A.pre) v = Fr::mul(v, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i, L) : i)));
-    sm.put(x, v);  // x is exactly the shared-memory slot for this layout
-  }
-  __syncthreads();
-
-  // ---- k radix-2 levels
   const uint32_t nbf = T >> 1;
   for (int step = 0; step < k; step++) {
+    const bool first = step == 0, last = step == k - 1;
     const int lb = DIT ? step : (k - 1 - step);  // local partner bit
     const int pb = b0 + lb;                      // global partner bit
     const uint32_t lbmask = (1u << lb) - 1u;
@@ -127,43 +121,58 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
       uint32_t r, c;
       if (TFAST) { r = q & ((rows >> 1) - 1); c = q >> (k - 1); }
       else { c = q & ((1u << logc) - 1); r = q >> logc; }
-      uint32_t t0 = ((r >> lb) << (lb + 1)) | (r & lbmask);
-      uint32_t t1 = t0 | (1u << lb);
-      uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
-      uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
-      Fr xv = sm.get(s0), yv = sm.get(s1);
-      if (pb == 0) {  // the level whose twiddles are all w^0 = 1: no products (warp-uniform branch)
-        sm.put(s0, Fr::add(xv, yv));
-        sm.put(s1, Fr::sub(xv, yv));
-        continue;
-      }
-      uint32_t u = (tile << logc) + c;
-      uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
-      uint32_t e = j << (L - 1 - pb);
-      Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
-      if (DIT) {
-        yv = Fr::mul(yv, w);
-        sm.put(s0, Fr::add(xv, yv));
-        sm.put(s1, Fr::sub(xv, yv));
+      const uint32_t t0 = ((r >> lb) << (lb + 1)) | (r & lbmask);
+      const uint32_t t1 = t0 | (1u << lb);
+      const uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
+      const uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
+      const uint32_t u = (tile << logc) + c;
+      const uint32_t ibase = ((u >> b0) << (b0 + k)) | (u & lowmask);
+      const uint32_t i0 = ibase | (t0 << b0), i1 = ibase | (t1 << b0);  // global indices of the two operands
+      Fr xv, yv;
+      if (first) {
+        xv = ld_fr(data + i0);
+        yv = ld_fr(data + i1);
+        if (A.pre) {
+          xv = Fr::mul(xv, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i0, L) : i0)));
+          yv = Fr::mul(yv, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i1, L) : i1)));
+        }
       } else {
-        sm.put(s0, Fr::add(xv, yv));
-        sm.put(s1, Fr::mul(Fr::sub(xv, yv), w));
+        xv = sm.get(s0);
+        yv = sm.get(s1);
+      }
+      Fr o0, o1;
+      if (pb == 0) {  // the level whose twiddles are all w^0 = 1: no products (warp-uniform branch)
+        o0 = Fr::add(xv, yv);
+        o1 = Fr::sub(xv, yv);
+      } else {
+        const uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
+        const uint32_t e = j << (L - 1 - pb);
+        const Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
+        if (DIT) {
+          yv = Fr::mul(yv, w);
+          o0 = Fr::add(xv, yv);
+          o1 = Fr::sub(xv, yv);
+        } else {
+          o0 = Fr::add(xv, yv);
+          o1 = Fr::mul(Fr::sub(xv, yv), w);
+        }
+      }
+      if (last) {
+        if (A.post_mode == 1) {
+          o0 = Fr::mul(o0, A.post_const);
+          o1 = Fr::mul(o1, A.post_const);
+        } else if (A.post_mode == 2) {
+          o0 = Fr::mul(o0, ldg_fr(post + (A.post_bitrev ? bitrev_dev(i0, L) : i0)));
+          o1 = Fr::mul(o1, ldg_fr(post + (A.post_bitrev ? bitrev_dev(i1, L) : i1)));
+        }
+        st_fr(data + i0, o0);
+        st_fr(data + i1, o1);
+      } else {
+        sm.put(s0, o0);
+        sm.put(s1, o1);
       }
     }
-    __syncthreads();
-  }
-
-  // ---- store
-  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
-    uint32_t t, c;
-    if (TFAST) { t = x & (rows - 1); c = x >> k; }
-    else { c = x & ((1u << logc) - 1); t = x >> logc; }
-    uint32_t u = (tile << logc) + c;
-    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
-    Fr v = sm.get(x);
-    if (A.post_mode == 1) v = Fr::mul(v, A.post_const);
-    else if (A.post_mode == 2) v = Fr::mul(v, ldg_fr(A.post + (A.post_bitrev ? bitrev_dev(i, L) : i)));
-    st_fr(data + i, v);
+    if (!last) __syncthreads();
   }
 }
 
@@ -172,6 +181,14 @@ __global__ void __launch_bounds__(256) k_geom_expand(Fr* __restrict__ t, uint32_
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s || s + i >= limit) return;
   st_fr(t + s + i, Fr::mul(ld_fr(t + i), step));
+}
+
+// a[i] = a[i] * b[i] - c[i]   (computeH with the 1 / (g^N - 1) factor folded into the transforms' scaling tables)
+__global__ void __launch_bounds__(256) k_h_pointwise_plain(Fr* __restrict__ a, const Fr* __restrict__ b,
+                                                            const Fr* __restrict__ c, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fr(a + i, Fr::sub(Fr::mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i)));
 }
 
 // a[i] = (a[i] * b[i] - c[i]) * den
@@ -204,6 +221,8 @@ static Fr fr_from_u64(uint64_t v) {
   r.l[1] = (uint32_t)(v >> 32);
   return Fr::to_mont(r);
 }
+
+static Fr coset_denominator_inv(size_t n);
 
 // Build t[0..count) = first * ratio^i on the device.
 static int build_geometric(b200g16_ctx* ctx, Fr* d_t, size_t count, const Fr& first, Fr ratio) {
@@ -266,8 +285,10 @@ static int ensure_coset(b200g16_ctx* ctx, int L) {
 
 // In-place transform of `batch` vectors of 2^L elements: consecutive at d_data, or (vecs != nullptr,
 // batch <= 3) at vecs[0..batch) — computeH transforms a, b, c in one launch per pass.
+// fused_post: per-vector tables multiplied in on the last store INSTEAD of the transform's own 1/N (plain inverse
+// transforms only); skip_pre: a forward coset transform whose g^i scaling the previous transform already applied.
 static int ntt_device_impl(b200g16_ctx* ctx, Fr* d_data, Fr* const* vecs, int L, int batch, bool inverse, bool coset,
-                           int decimation) {
+                           int decimation, const Fr* const* fused_post = nullptr, bool skip_pre = false) {
   if (L < 0 || L > 28) return fail(B200G16_ERR_ARG, "ntt: log2n=%d out of range (two-adicity 28)", L);
   if (decimation != B200G16_DIF && decimation != B200G16_DIT) return fail(B200G16_ERR_ARG, "ntt: bad decimation");
   if (batch < 1) return fail(B200G16_ERR_ARG, "ntt: batch");
@@ -291,13 +312,19 @@ static int ntt_device_impl(b200g16_ctx* ctx, Fr* d_data, Fr* const* vecs, int L,
   A.post_const = dom.n_inv;
 
   // forward-coset scaling on the first load, inverse scaling on the last store
-  const Fr* pre = (coset && !inverse) ? ws.coset.as<Fr>() : nullptr;
+  const Fr* pre = (coset && !inverse && !skip_pre) ? ws.coset.as<Fr>() : nullptr;
   const int pre_bitrev = dit ? 1 : 0;        // DIT input is bit-reversed
   int post_mode = 0;
   const Fr* post = nullptr;
   if (inverse) {
     if (coset) { post_mode = 2; post = ws.coset.as<Fr>() + n; }
     else post_mode = 1;
+  }
+  for (int i = 0; i < 3; i++) A.post_vec[i] = nullptr;
+  if (fused_post) {
+    if (!inverse || coset || !vecs) return fail(B200G16_ERR_ARG, "ntt: fused scaling needs a plain inverse transform over a vector list");
+    post_mode = 2;
+    for (int i = 0; i < batch && i < 3; i++) A.post_vec[i] = fused_post[i];
   }
   const int post_bitrev = dit ? 0 : 1;       // DIF output is bit-reversed
 
@@ -365,21 +392,72 @@ int h_pointwise_device(b200g16_ctx* ctx, Fr* a, const Fr* b, const Fr* c, int L)
   return 0;
 }
 
-// computeH on device buffers a,b,c (each 2^L elements, already zero-padded); result in a.
-int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time) {
+// fused scaling tables for computeH at size 2^L: t1[i] = g^i / N, t2[i] = g^i / (N (g^N - 1))
+static int ensure_fused(b200g16_ctx* ctx, int L) {
+  NttWorkspace& ws = ctx->ntt;
+  if (ws.fused_log == L) return 0;
+  size_t n = (size_t)1 << L;
+  B200_TRY(ws.fused.ensure(2 * n * sizeof(Fr)));
+  const uint32_t g[8] = B200_FR_GEN;
+  NttDomain d;
+  domain_params(L, &d);
+  B200_TRY(build_geometric(ctx, ws.fused.as<Fr>(), n, d.n_inv, fr_from_limbs(g)));
+  B200_TRY(build_geometric(ctx, ws.fused.as<Fr>() + n, n, Fr::mul(d.n_inv, coset_denominator_inv(n)), fr_from_limbs(g)));
+  ws.fused_log = L;
+  return 0;
+}
+
+// The first two transforms of computeH for `batch` vectors (<= 3), fused: FFTInverse (DIF) stores x / N * g^i
+// [* 1/(g^N - 1) when with_den[v]] in one product, so the coset FFT (DIT) that follows loads without scaling.
+// Same values as ntt(inverse) ; ntt(coset) [; * den], one Fr product per element less (two with the denominator).
+int ntt_coset_pair_device(b200g16_ctx* ctx, Fr* const* vecs, int batch, int L, const bool* with_den) {
+  if (L == 0) {  // one element: iNTT and coset NTT are the identity; only the denominator remains
+    for (int v = 0; v < batch; v++)
+      if (with_den[v]) {
+        Fr x;
+        B200_CUDA(cudaMemcpyAsync(&x, vecs[v], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        x = Fr::mul(x, coset_denominator_inv(1));
+        B200_CUDA(cudaMemcpyAsync(vecs[v], &x, sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+    return 0;
+  }
+  B200_TRY(ensure_twiddles(ctx, L));
+  B200_TRY(ensure_coset(ctx, L));
+  B200_TRY(ensure_fused(ctx, L));
   const size_t n = (size_t)1 << L;
+  const Fr* post[3] = {nullptr, nullptr, nullptr};
+  for (int v = 0; v < batch; v++) post[v] = ctx->ntt.fused.as<Fr>() + (with_den[v] ? n : 0);
+  B200_TRY(ntt_device_impl(ctx, nullptr, vecs, L, batch, true, false, B200G16_DIF, post, false));
+  return ntt_device_impl(ctx, nullptr, vecs, L, batch, false, true, B200G16_DIT, nullptr, true);
+}
+
+// a = a * b - c on coset evaluations whose a and c already carry 1 / (g^N - 1)
+int h_pointwise_plain_device(b200g16_ctx* ctx, Fr* a, const Fr* b, const Fr* c, int L) {
+  const size_t n = (size_t)1 << L;
+  k_h_pointwise_plain<<<cdiv_u(n, 256), 256, 0, ctx->stream>>>(a, b, c, (uint32_t)n);
+  ctx->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// computeH on device buffers a,b,c (each 2^L elements, already zero-padded); result in a.
+// (a b - c) / (g^N - 1) = (a / d) b - (c / d): the denominator rides on the fused scaling of a and c.
+int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and_time) {
   int ev = 0;
   auto mark = [&]() { if (sync_and_time && ev < 18) cudaEventRecord(ctx->ev[ev++], ctx->stream); };
   // warm the tables outside the timed phases
   B200_TRY(ensure_twiddles(ctx, L));
   B200_TRY(ensure_coset(ctx, L));
+  if (L > 0) B200_TRY(ensure_fused(ctx, L));
   mark();
   Fr* v[3] = {a, b, c};
-  B200_TRY(ntt_device_impl(ctx, nullptr, v, L, 3, true, false, B200G16_DIF));
+  const bool den[3] = {true, false, true};
+  B200_TRY(ntt_coset_pair_device(ctx, v, 3, L, den));
   mark();
-  B200_TRY(ntt_device_impl(ctx, nullptr, v, L, 3, false, true, B200G16_DIT));
   mark();
-  B200_TRY(h_pointwise_device(ctx, a, b, c, L));
+  B200_TRY(h_pointwise_plain_device(ctx, a, b, c, L));
   mark();
   B200_TRY(ntt_device(ctx, a, L, 1, true, true, B200G16_DIF));
   mark();

@@ -64,7 +64,11 @@ def _worker(rank, world, port, n, q):
     partial = cport.msm_g1(pts[lo:hi], sc[lo:hi], 1)          # stands in for the per-GPU MSM
     total = sharded.exchange_and_combine(partial, group=1)
     exp = bn.g1_mul(bn.G1_GEN, sum(s * (k0 + i * d) for i, s in enumerate(ss)) % R)
-    q.put((rank, bn.g1_from_array(total)[0] == exp))
+    xch = sharded.PointExchange(8)                            # the preallocated exchange bench.py steps through
+    same = all(np.array_equal(xch.combine(partial, 1), total) for _ in range(3))
+    recs = xch.gather(np.full(8, rank + 1, dtype=np.uint64))
+    same = same and recs.shape == (world, 8) and all((recs[r] == r + 1).all() for r in range(world))
+    q.put((rank, bn.g1_from_array(total)[0] == exp and same))
     dist.barrier()
     dist.destroy_process_group()
 
