@@ -244,12 +244,17 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->tail_stream);
   std::vector<DevBuf*> bufs = {&ctx->msm.scalars, &ctx->msm.digits, &ctx->msm.entries, &ctx->ntt.a, &ctx->ntt.b,
-                               &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->ntt.fused, &ctx->io_a,  &ctx->io_b,
+                               &ctx->ntt.c,       &ctx->ntt.tw,     &ctx->ntt.coset,   &ctx->ntt.fused, &ctx->ntt.dist, &ctx->io_a,  &ctx->io_b,
                                &ctx->io_c};
   for (int i = 0; i < MSM_SETS; i++)
     for (DevBuf* b : {&ctx->msm.counts[i], &ctx->msm.partials[i], &ctx->msm.chunks[i], &ctx->msm.misc[i], &ctx->msm.tasks[i]})
       bufs.push_back(b);
   for (DevBuf* b : bufs) b->release();
+  for (int v = 0; v < 3; v++) {
+    for (int d = 0; d < 8; d++)
+      if (ctx->dist_h.ipc_opened[v][d]) cudaIpcCloseMemHandle(ctx->dist_h.peers[v][d]);
+    ctx->dist_h.slice[v].release();
+  }
   if (ctx->msm.pinned) cudaFreeHost(ctx->msm.pinned);
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < MSM_SETS; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }

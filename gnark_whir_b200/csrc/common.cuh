@@ -75,10 +75,11 @@ struct MsmWorkspace {
 };
 
 struct NttWorkspace {
-  DevBuf a, b, c, tw, coset, fused;
+  DevBuf a, b, c, tw, coset, fused, dist;
   int tw_log = -1;     // twiddle table covers 2^tw_log
   int coset_log = -1;  // coset tables built for exactly 2^coset_log
   int fused_log = -1;  // computeH's fused scaling tables (g^i / N with and without 1 / (g^N - 1))
+  int dist_log = -1, dist_g = 0, dist_me = -1;  // compact scaling tables of the multi-GPU computeH (this device's slice)
 };
 
 // descriptor of a window table attached to a bases vector (b200g16_bases_precompute)
@@ -114,6 +115,16 @@ struct MsmSorted {
   bool valid = false;
 };
 
+// computeH split over 2 / 4 / 8 devices: this device's slices of a, b, c (their own allocations: exported to the other
+// processes / devices and never reallocated while open) and the peers' slices as seen from this device
+struct DistH {
+  int g = 0, me = 0, L = 0;
+  DevBuf slice[3];
+  void* peers[3][8] = {};    // peers[v][d]; peers[v][me] == slice[v].p
+  bool ipc_opened[3][8] = {};
+  bool ready = false;        // every peer pointer set
+};
+
 struct Timings {
   // last-call device timings in ms (CUDA events on ctx stream); index = phase
   float ms[16];
@@ -142,6 +153,7 @@ struct b200g16_ctx {
   std::mutex mu;  // one call at a time per ctx (gnark calls MSMs from several goroutines)
   b200::MsmWorkspace msm;
   b200::NttWorkspace ntt;
+  b200::DistH dist_h;
   b200::DevBuf io_a, io_b, io_c;  // staging for host-pointer entry points
   b200::Timings timings = {};
   int msm_window_override = 0;  // 0 = auto

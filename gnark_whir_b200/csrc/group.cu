@@ -25,6 +25,7 @@ struct b200g16_group {
   std::vector<int> devices;
   cudaEvent_t ev_vec[3] = {nullptr, nullptr, nullptr};  // coset evaluations of a / b / c ready on their owner
   cudaEvent_t ev_h = nullptr;                           // h ready on the root
+  std::vector<cudaEvent_t> ev_stage[4];                 // distributed computeH: stage s enqueued on device i
   std::mutex mu;                                        // one group call at a time
 };
 
@@ -67,6 +68,29 @@ struct Flag {
     return status;
   }
 };
+
+// all device threads meet here between the stages of a distributed computeH; a failing thread keeps arriving (with
+// its status) so nobody waits forever, and everybody learns that somebody failed
+struct Barrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, count = 0, gen = 0, status = 0;
+  explicit Barrier(int n_) : n(n_) {}
+  int arrive(int st) {
+    std::unique_lock<std::mutex> l(m);
+    if (st && !status) status = st;
+    const int my = gen;
+    if (++count == n) { count = 0; gen++; cv.notify_all(); }
+    else cv.wait(l, [&] { return gen != my; });
+    return status;
+  }
+};
+
+int log2_of(int n) {
+  for (int g = 0; g < 6; g++)
+    if ((1 << g) == n) return g;
+  return -1;
+}
 
 // fn(i) on one thread per device; the first failing device's status and message become the caller's
 template <class Fn>
@@ -123,6 +147,13 @@ int b200g16_group_init(const int* devices, int n, b200g16_group** out) {
   }
   cudaSetDevice(devices[0]);
   B200_CUDA(cudaEventCreateWithFlags(&g->ev_h, cudaEventDisableTiming));
+  for (auto& evs : g->ev_stage) {
+    evs.assign(n, nullptr);
+    for (int i = 0; i < n; i++) {
+      cudaSetDevice(devices[i]);
+      B200_CUDA(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+    }
+  }
   *out = g;
   return 0;
 }
@@ -132,6 +163,9 @@ void b200g16_group_destroy(b200g16_group* g) {
   for (int v = 0; v < 3; v++)
     if (g->ev_vec[v]) cudaEventDestroy(g->ev_vec[v]);
   if (g->ev_h) cudaEventDestroy(g->ev_h);
+  for (auto& evs : g->ev_stage)
+    for (auto e : evs)
+      if (e) cudaEventDestroy(e);
   for (auto* c : g->ctx) b200g16_destroy(c);
   delete g;
 }
@@ -271,6 +305,83 @@ void b200g16_group_pk_free(b200g16_group_pk* pk) {
   delete pk;
 }
 
+static int dist_h_alloc(b200g16_ctx* ctx, unsigned log2n, int n_peers, int me);
+
+// computeH split over all 2 / 4 / 8 devices of the group (ntt.cu: cross-GPU levels over peer memory), then the five
+// MSMs on every device's shard.  Stages are separated by a host barrier + cross-device event waits.
+static int group_prove_dist(b200g16_group* g, const b200g16_group_pk* gpk, const uint64_t* wires, size_t n_wires,
+                            const uint64_t* const* src, size_t n_constraints, const Fr& fr_r, const Fr& fr_s,
+                            std::vector<b200g16_proof>& parts) {
+  const int n = g->n, L = (int)gpk->log2n, gl = log2_of(n);
+  const size_t M = ((size_t)1 << L) >> gl;
+  Barrier bar(n);
+  return run_on_all(g, [&](int i) -> int {
+    b200g16_ctx* ctx = g->ctx[i];
+    const b200g16_pk* pk = gpk->shard[i];
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    cudaStream_t stm = ctx->stream;
+    int ev = 0;
+    auto wait_all = [&](int stage) -> int {
+      for (int j = 0; j < n; j++) B200_CUDA(cudaStreamWaitEvent(stm, g->ev_stage[stage][j], 0));
+      return 0;
+    };
+    // ---- allocate / publish slices
+    int st = [&]() -> int {
+      B200_CUDA(cudaSetDevice(ctx->device));
+      return dist_h_alloc(ctx, (unsigned)L, n, i);
+    }();
+    st = bar.arrive(st);
+    if (!st) st = [&]() -> int {
+      DistH& D = ctx->dist_h;
+      for (int d = 0; d < n; d++)
+        for (int v = 0; v < 3; v++) D.peers[v][d] = g->ctx[d]->dist_h.slice[v].p;
+      D.ready = true;
+      cudaEventRecord(ctx->ev[ev++], stm);
+      // witness on the copy stream, this device's slices of a, b, c (zero padded) on the main stream
+      B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
+      B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      B200_CUDA(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
+      const size_t lo = (size_t)i * M;
+      const size_t have = n_constraints > lo ? (n_constraints - lo < M ? n_constraints - lo : M) : 0;
+      for (int v = 0; v < 3; v++) {
+        char* dst = (char*)D.slice[v].p;
+        if (have) B200_CUDA(cudaMemcpyAsync(dst, src[v] + lo * 4, have * sizeof(Fr), cudaMemcpyHostToDevice, stm));
+        if (have < M) B200_CUDA(cudaMemsetAsync(dst + have * sizeof(Fr), 0, (M - have) * sizeof(Fr), stm));
+      }
+      B200_CUDA(cudaEventRecord(g->ev_stage[0][i], stm));
+      return 0;
+    }();
+    // ---- the four phases of the distributed computeH
+    for (int phase = 0; phase < 4; phase++) {
+      st = bar.arrive(st);
+      if (!st) st = [&]() -> int {
+        B200_TRY(wait_all(phase));   // every device has enqueued (and will have finished) the previous stage
+        DistH& D = ctx->dist_h;
+        B200_TRY(compute_h_dist_phase(ctx, reinterpret_cast<Fr* const (*)[8]>(D.peers), D.g, D.me, D.L, phase));
+        if (phase < 3) B200_CUDA(cudaEventRecord(g->ev_stage[phase + 1][i], stm));
+        return 0;
+      }();
+    }
+    // ---- the MSMs on this device's shard; h slice = this device's a slice
+    if (!st) st = [&]() -> int {
+      B200_CUDA(cudaStreamWaitEvent(stm, ctx->ev_copy[1], 0));
+      cudaEventRecord(ctx->ev[ev++], stm);
+      B200_TRY(prove_front(ctx, pk, ctx->io_a.as<Fr>(), &ev));
+      if (ev < 18) cudaEventRecord(ctx->ev[ev++], stm);
+      const Fr* d_h = reinterpret_cast<const Fr*>(ctx->dist_h.slice[0].p) - pk->off_z;  // prove_back reads d_h[off_z, off_z + n_z)
+      B200_TRY(prove_back(ctx, pk, d_h, fr_r, fr_s, &parts[i], &ev));
+      ctx->timings.n = ev - 1;
+      for (int k = 0; k + 1 < ev; k++) cudaEventElapsedTime(&ctx->timings.ms[k], ctx->ev[k], ctx->ev[k + 1]);
+      return 0;
+    }();
+    if (st) ctx->prove_active = false;
+    // nobody may reuse (or free) its slices while a peer's cross kernel could still read them
+    cudaStreamSynchronize(stm);
+    st = bar.arrive(st);
+    return st;
+  });
+}
+
 // ---- the prove
 int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uint64_t* wires, size_t n_wires,
                         const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints, const uint64_t r[4],
@@ -289,11 +400,21 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
   const uint64_t* src[3] = {a, b, c};
   Flag vec_ready[3], h_ready;
   std::vector<b200g16_proof> parts(n);
+  const int gl = log2_of(n);
+  const bool dist = gl >= 1 && gl <= 3 && L >= 2 * gl + 1;
+  for (int i = 0; dist && i < n; i++) {   // the h slices must coincide with the Z shards (true for whole keys: n_z = N - 1)
+    const b200g16_pk* pk = gpk->shard[i];
+    if (pk->off_z != (size_t)i * (N >> gl) || pk->n_z > (N >> gl)) return fail(B200G16_ERR_STATE, "group_prove: Z shard %d does not match its h slice", i);
+  }
+  int st = 0;
+  if (dist) {
+    st = group_prove_dist(g, gpk, wires, n_wires, src, n_constraints, fr_r, fr_s, parts);
+  } else {
   auto abort_all = [&](int st) {
     for (auto& f : vec_ready) f.signal(st);
     h_ready.signal(st);
   };
-  int st = run_on_all(g, [&](int i) -> int {
+  st = run_on_all(g, [&](int i) -> int {
     auto body = [&]() -> int {
       b200g16_ctx* ctx = g->ctx[i];
       const b200g16_pk* pk = gpk->shard[i];
@@ -361,6 +482,7 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
     }
     return rc;
   });
+  }
   if (st) {
     for (int i = 0; i < n; i++) { cudaSetDevice(g->ctx[i]->device); cudaStreamSynchronize(g->ctx[i]->stream); }
     return st;
@@ -379,11 +501,121 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
   G2Affine b2 = host_sum_points<Fp2>(p2.data(), n);
   B200_TRY(b200g16_prove_finish(gpk->shard[0], (const uint64_t*)&sums[0], (const uint64_t*)&sums[1], (const uint64_t*)&sums[2],
                                 (const uint64_t*)&sums[3], (const uint64_t*)&b2, r, s, proof_out));
-  if (h_out) {
+  if (h_out && dist) {
+    const size_t M = N >> gl;
+    for (int i = 0; i < n; i++) {
+      B200_CUDA(cudaSetDevice(g->ctx[i]->device));
+      B200_CUDA(cudaMemcpy(h_out + (size_t)i * M * 4, g->ctx[i]->dist_h.slice[0].p, M * sizeof(Fr), cudaMemcpyDeviceToHost));
+    }
+  } else if (h_out) {
     B200_CUDA(cudaSetDevice(g->ctx[root]->device));
     B200_CUDA(cudaMemcpy(h_out, g->ctx[root]->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));
   }
   return 0;
+}
+
+// ---- computeH split over 2 / 4 / 8 GPUs, one PROCESS per GPU (torch.distributed ranks): CUDA IPC maps every
+// rank's slices into every other rank, the cross-GPU butterfly levels run as kernels over that peer memory
+// (ntt.cu k_ntt_cross / k_ntt_cross_h), and the caller separates the four phases by barriers.
+static int dist_h_alloc(b200g16_ctx* ctx, unsigned log2n, int n_peers, int me) {
+  const int g = log2_of(n_peers);
+  if (g < 1 || g > 3) return fail(B200G16_ERR_ARG, "dist_h: %d peers (2, 4 or 8)", n_peers);
+  if (log2n > 28 || (int)log2n < 2 * g + 1) return fail(B200G16_ERR_ARG, "dist_h: 2^%u elements over %d devices", log2n, n_peers);
+  if (me < 0 || me >= n_peers) return fail(B200G16_ERR_ARG, "dist_h: rank %d of %d", me, n_peers);
+  DistH& D = ctx->dist_h;
+  if (D.g && (D.L != (int)log2n || D.g != g || D.me != me)) return fail(B200G16_ERR_STATE, "dist_h: already set up for another shape; close first");
+  const size_t M = (size_t)1 << (log2n - g);
+  for (int v = 0; v < 3; v++) {
+    B200_TRY(D.slice[v].ensure(M * sizeof(Fr)));
+    D.peers[v][me] = D.slice[v].p;
+  }
+  D.g = g; D.me = me; D.L = (int)log2n;
+  D.ready = false;
+  return 0;
+}
+
+int b200g16_dist_h_init(b200g16_ctx* ctx, unsigned log2n, int n_peers, int me, uint8_t* handles_out) {
+  if (!ctx || !handles_out) return fail(B200G16_ERR_ARG, "dist_h_init: null");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  B200_TRY(dist_h_alloc(ctx, log2n, n_peers, me));
+  for (int v = 0; v < 3; v++) {
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, ctx->dist_h.slice[v].p));
+    memcpy(handles_out + 64 * v, &h, 64);
+  }
+  return 0;
+}
+
+int b200g16_dist_h_open(b200g16_ctx* ctx, const uint8_t* all_handles) {
+  if (!ctx || !all_handles) return fail(B200G16_ERR_ARG, "dist_h_open: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  DistH& D = ctx->dist_h;
+  if (!D.g) return fail(B200G16_ERR_STATE, "dist_h_open: call b200g16_dist_h_init first");
+  const int G = 1 << D.g;
+  for (int d = 0; d < G; d++) {
+    if (d == D.me) continue;
+    for (int v = 0; v < 3; v++) {
+      if (D.ipc_opened[v][d]) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all_handles + ((size_t)d * 3 + v) * 64, 64);
+      void* p = nullptr;
+      B200_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      D.peers[v][d] = p;
+      D.ipc_opened[v][d] = true;
+    }
+  }
+  D.ready = true;
+  return 0;
+}
+
+void* b200g16_dist_h_slice(b200g16_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 2 || !ctx->dist_h.g) return nullptr;
+  return ctx->dist_h.slice[which].p;
+}
+
+int b200g16_dist_h_load(b200g16_ctx* ctx, const void* d_a, const void* d_b, const void* d_c) {
+  if (!ctx || !d_a || !d_b || !d_c) return fail(B200G16_ERR_ARG, "dist_h_load: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  DistH& D = ctx->dist_h;
+  if (!D.g) return fail(B200G16_ERR_STATE, "dist_h_load: call b200g16_dist_h_init first");
+  const size_t bytes = (((size_t)1 << D.L) >> D.g) * sizeof(Fr);
+  const void* src[3] = {d_a, d_b, d_c};
+  for (int v = 0; v < 3; v++)
+    B200_CUDA(cudaMemcpyAsync(D.slice[v].p, src[v], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int b200g16_dist_h_phase(b200g16_ctx* ctx, int phase) {
+  if (!ctx) return fail(B200G16_ERR_ARG, "dist_h_phase: null");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  DistH& D = ctx->dist_h;
+  if (!D.ready) return fail(B200G16_ERR_STATE, "dist_h_phase: peers not opened");
+  B200_TRY(compute_h_dist_phase(ctx, reinterpret_cast<Fr* const (*)[8]>(D.peers), D.g, D.me, D.L, phase));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void b200g16_dist_h_close(b200g16_ctx* ctx) {
+  if (!ctx) return;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DistH& D = ctx->dist_h;
+  for (int v = 0; v < 3; v++)
+    for (int d = 0; d < 8; d++) {
+      if (D.ipc_opened[v][d]) cudaIpcCloseMemHandle(D.peers[v][d]);
+      D.ipc_opened[v][d] = false;
+      D.peers[v][d] = nullptr;
+    }
+  for (int v = 0; v < 3; v++) D.slice[v].release();
+  D.g = 0;
+  D.ready = false;
 }
 
 }  // extern "C"

@@ -176,6 +176,104 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
   }
 }
 
+// ------------------------------------------------------------------------------ transforms split over G = 2^g GPUs
+// Device d holds positions [d M, (d + 1) M) of a vector of N = 2^L elements (M = N / G).  The g levels whose partner
+// bit lies among the top g position bits pair elements at the SAME local offset on different devices; every other
+// level is local and — because w_N^(e G) = w_M^e — is exactly a level of the ordinary size-M transform of the
+// slice.  So a DIF transform is [cross levels] + [local size-M DIF], a DIT transform [local size-M DIT] +
+// [cross levels], with unchanged global orderings (natural <-> bit-reversed, sliced by position).
+// The cross levels run as ONE kernel per device over peer memory: device `me` takes the offsets
+// [me M / G, (me + 1) M / G), loads the G elements of each offset from the G devices' buffers (NVLink peer loads,
+// coalesced), runs the g butterfly levels in registers and stores the results back to their owners.  Every
+// element is read and written by exactly one device, so the only synchronisation is "all slices ready" before and
+// "all cross kernels done" after (events in one process, a barrier between processes).
+struct CrossArgs {
+  Fr* buf[3][8];    // [vector][device] slice base pointers, valid on this device
+  const Fr* tw;
+  uint32_t tw_half;
+  int tw_sh;
+  int L, me;
+  int inverse;      // twiddles w^-e
+};
+
+template <int GLOG, bool DIT>
+__device__ __forceinline__ void cross_levels(Fr (&x)[1 << GLOG], uint32_t o, const Fr* __restrict__ tw, int tw_sh,
+                                             uint32_t tw_half, int L, bool inverse) {
+  constexpr int G = 1 << GLOG;
+  const uint32_t M = 1u << (L - GLOG);
+#pragma unroll
+  for (int step = 0; step < GLOG; step++) {
+    const int q = DIT ? (GLOG - 1 - step) : step;   // level q pairs device indices that differ in bit GLOG-1-q
+    const int bit = GLOG - 1 - q;
+#pragma unroll
+    for (int d0 = 0; d0 < G; d0++) {
+      if (d0 & (1 << bit)) continue;
+      const int d1 = d0 | (1 << bit);
+      const uint32_t j = (uint32_t)(d0 & ((1 << bit) - 1)) * M + o;   // position bits below the partner bit
+      const uint32_t e = j << q;
+      Fr a = x[d0], b = x[d1];
+      if (e == 0 && !inverse) {
+        x[d0] = Fr::add(a, b);
+        x[d1] = Fr::sub(a, b);
+        continue;
+      }
+      const Fr w = twiddle(tw, e, tw_sh, tw_half, inverse);
+      if (DIT) {
+        b = Fr::mul(b, w);
+        x[d0] = Fr::add(a, b);
+        x[d1] = Fr::sub(a, b);
+      } else {
+        x[d0] = Fr::add(a, b);
+        x[d1] = Fr::mul(Fr::sub(a, b), w);
+      }
+    }
+  }
+}
+
+template <int GLOG, bool DIT>
+__global__ void __launch_bounds__(128) k_ntt_cross(CrossArgs A) {
+  constexpr int G = 1 << GLOG;
+  const uint32_t share = (1u << (A.L - GLOG)) >> GLOG;           // offsets per device
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= share) return;
+  const uint32_t o = (uint32_t)A.me * share + t;
+  Fr x[G];
+#pragma unroll
+  for (int d = 0; d < G; d++) x[d] = ld_fr(A.buf[blockIdx.y][d] + o);
+  cross_levels<GLOG, DIT>(x, o, A.tw, A.tw_sh, A.tw_half, A.L, A.inverse != 0);
+#pragma unroll
+  for (int d = 0; d < G; d++) st_fr(A.buf[blockIdx.y][d] + o, x[d]);
+}
+
+// computeH's middle, fused over peer memory: last (cross) levels of the coset FFTs of a, b, c, the pointwise
+// a b - c (a and c already carry 1 / (g^N - 1)), and the first (cross) levels of the final inverse transform;
+// reads 3 vectors, writes 1 (into the a slices).
+template <int GLOG>
+__global__ void __launch_bounds__(128) k_ntt_cross_h(CrossArgs A) {
+  constexpr int G = 1 << GLOG;
+  const uint32_t share = (1u << (A.L - GLOG)) >> GLOG;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= share) return;
+  const uint32_t o = (uint32_t)A.me * share + t;
+  Fr acc[G], x[G];
+#pragma unroll
+  for (int d = 0; d < G; d++) acc[d] = ld_fr(A.buf[0][d] + o);
+  cross_levels<GLOG, true>(acc, o, A.tw, A.tw_sh, A.tw_half, A.L, false);
+#pragma unroll
+  for (int d = 0; d < G; d++) x[d] = ld_fr(A.buf[1][d] + o);
+  cross_levels<GLOG, true>(x, o, A.tw, A.tw_sh, A.tw_half, A.L, false);
+#pragma unroll
+  for (int d = 0; d < G; d++) acc[d] = Fr::mul(acc[d], x[d]);
+#pragma unroll
+  for (int d = 0; d < G; d++) x[d] = ld_fr(A.buf[2][d] + o);
+  cross_levels<GLOG, true>(x, o, A.tw, A.tw_sh, A.tw_half, A.L, false);
+#pragma unroll
+  for (int d = 0; d < G; d++) acc[d] = Fr::sub(acc[d], x[d]);
+  cross_levels<GLOG, false>(acc, o, A.tw, A.tw_sh, A.tw_half, A.L, true);
+#pragma unroll
+  for (int d = 0; d < G; d++) st_fr(A.buf[0][d] + o, acc[d]);
+}
+
 // t[s + i] = t[i] * step  for i < s   (doubling construction of geometric tables)
 __global__ void __launch_bounds__(256) k_geom_expand(Fr* __restrict__ t, uint32_t s, uint32_t limit, Fr step) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,6 +565,93 @@ int compute_h_device(b200g16_ctx* ctx, Fr* a, Fr* b, Fr* c, int L, bool sync_and
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   return 0;
+}
+
+// ---- computeH over G = 2^g devices (see the kernels above) ------------------------------------------------------
+static uint32_t bitrev_host(uint32_t v, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+  return r;
+}
+
+// Compact scaling tables of device `me`: position d M + o (bit-reversed order) has natural index
+// bitrev_{L-g}(o) G + bitrev_g(me), so the size-M tables  t1[k] = g^(k G + br) / N,  t2 = t1 / (g^N - 1),
+// ti[k] = g^-(k G + br) / N  are read at k = bitrev(o) by the ordinary size-M passes.
+static int ensure_dist_tables(b200g16_ctx* ctx, int L, int g, int me) {
+  NttWorkspace& ws = ctx->ntt;
+  if (ws.dist_log == L && ws.dist_g == g && ws.dist_me == me) return 0;
+  const size_t M = (size_t)1 << (L - g);
+  B200_TRY(ws.dist.ensure(3 * M * sizeof(Fr)));
+  const uint32_t gen[8] = B200_FR_GEN;
+  const uint32_t gen_inv[8] = B200_FR_GEN_INV;
+  NttDomain d;
+  domain_params(L, &d);
+  const uint64_t br = bitrev_host((uint32_t)me, g), G = (uint64_t)1 << g;
+  const Fr gf = fr_from_limbs(gen), gi = fr_from_limbs(gen_inv);
+  const Fr first = Fr::mul(d.n_inv, fr_pow_u64(gf, br));
+  B200_TRY(build_geometric(ctx, ws.dist.as<Fr>(), M, first, fr_pow_u64(gf, G)));
+  B200_TRY(build_geometric(ctx, ws.dist.as<Fr>() + M, M, Fr::mul(first, coset_denominator_inv((size_t)1 << L)), fr_pow_u64(gf, G)));
+  B200_TRY(build_geometric(ctx, ws.dist.as<Fr>() + 2 * M, M, Fr::mul(d.n_inv, fr_pow_u64(gi, br)), fr_pow_u64(gi, G)));
+  ws.dist_log = L; ws.dist_g = g; ws.dist_me = me;
+  return 0;
+}
+
+static int fill_cross_args(b200g16_ctx* ctx, CrossArgs* A, Fr* const (*peers)[8], int nvec, int g, int me, int L, bool inverse) {
+  B200_TRY(ensure_twiddles(ctx, L));
+  memset(A, 0, sizeof(*A));
+  for (int v = 0; v < nvec; v++)
+    for (int d = 0; d < (1 << g); d++) A->buf[v][d] = peers[v][d];
+  A->tw = ctx->ntt.tw.as<Fr>();
+  A->tw_sh = ctx->ntt.tw_log - L;
+  A->tw_half = (uint32_t)(((size_t)1 << ctx->ntt.tw_log) >> 1);
+  A->L = L;
+  A->me = me;
+  A->inverse = inverse ? 1 : 0;
+  return 0;
+}
+
+// One phase of the distributed computeH on this device (enqueued on ctx->stream, no synchronisation):
+//   0  cross levels of FFTInverse(a, b, c)                       (needs: every device's slices loaded)
+//   1  local: rest of FFTInverse with the fused scaling, then the local levels of the coset FFT
+//   2  cross levels of the coset FFTs + pointwise + cross levels of the last FFTInverse -> a slices
+//   3  local: rest of the last FFTInverse with g^-i / N  -> this device's slice of h in its a buffer
+// peers[v][d]: slice of vector v (0 = a, 1 = b, 2 = c) on device d, addressable from this device.
+int compute_h_dist_phase(b200g16_ctx* ctx, Fr* const (*peers)[8], int g, int me, int L, int phase) {
+  if (g < 1 || g > 3 || L - 2 * g < 0 || L > 28) return fail(B200G16_ERR_ARG, "compute_h_dist: 2^%d over 2^%d devices", L, g);
+  if (me < 0 || me >= (1 << g) || phase < 0 || phase > 3) return fail(B200G16_ERR_ARG, "compute_h_dist: bad rank / phase");
+  const int Lm = L - g;
+  const size_t M = (size_t)1 << Lm;
+  const uint32_t share = (uint32_t)(M >> g);
+  CrossArgs A;
+  if (phase == 0 || phase == 2) {
+    B200_TRY(fill_cross_args(ctx, &A, peers, 3, g, me, L, phase == 0));
+    dim3 grid(cdiv_u(share, 128), phase == 0 ? 3 : 1);
+    if (phase == 0) {
+      if (g == 1) k_ntt_cross<1, false><<<grid, 128, 0, ctx->stream>>>(A);
+      else if (g == 2) k_ntt_cross<2, false><<<grid, 128, 0, ctx->stream>>>(A);
+      else k_ntt_cross<3, false><<<grid, 128, 0, ctx->stream>>>(A);
+    } else {
+      if (g == 1) k_ntt_cross_h<1><<<grid, 128, 0, ctx->stream>>>(A);
+      else if (g == 2) k_ntt_cross_h<2><<<grid, 128, 0, ctx->stream>>>(A);
+      else k_ntt_cross_h<3><<<grid, 128, 0, ctx->stream>>>(A);
+    }
+    ctx->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
+  B200_TRY(ensure_twiddles(ctx, L));   // the size-N table also serves the size-M passes (stride 2^g)
+  B200_TRY(ensure_dist_tables(ctx, L, g, me));
+  const Fr* t = ctx->ntt.dist.as<Fr>();
+  if (phase == 1) {
+    Fr* v[3] = {peers[0][me], peers[1][me], peers[2][me]};
+    const Fr* post[3] = {t + M, t, t + M};   // a and c carry 1 / (g^N - 1)
+    if (Lm == 0) return fail(B200G16_ERR_ARG, "compute_h_dist: slices of one element");
+    B200_TRY(ntt_device_impl(ctx, nullptr, v, Lm, 3, true, false, B200G16_DIF, post, false));
+    return ntt_device_impl(ctx, nullptr, v, Lm, 3, false, true, B200G16_DIT, nullptr, true);
+  }
+  Fr* v[1] = {peers[0][me]};
+  const Fr* post[1] = {t + 2 * M};
+  return ntt_device_impl(ctx, nullptr, v, Lm, 1, true, false, B200G16_DIF, post, false);
 }
 
 }  // namespace b200

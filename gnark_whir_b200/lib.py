@@ -95,6 +95,12 @@ SIGNATURES = {
     "b200g16_group_pk_upload": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "b200g16_group_pk_free": (None, [_vp]),
     "b200g16_group_prove": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "b200g16_dist_h_init": (C.c_int, [_vp, C.c_uint, C.c_int, C.c_int, _vp]),
+    "b200g16_dist_h_open": (C.c_int, [_vp, _vp]),
+    "b200g16_dist_h_load": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "b200g16_dist_h_slice": (_vp, [_vp, C.c_int]),
+    "b200g16_dist_h_phase": (C.c_int, [_vp, C.c_int]),
+    "b200g16_dist_h_close": (None, [_vp]),
     "b200g16_g1_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g2_add": (C.c_int, [_vp, _vp, _vp]),
     "b200g16_g1_scalar_mul": (C.c_int, [_vp, _vp, _vp]),
@@ -606,6 +612,32 @@ class Context:
         out = ProofOut()
         _check(load().b200g16_prove_end_dev(self.h, pk, _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
+
+    # -- computeH split over 2 / 4 / 8 ranks (CUDA IPC peer memory; see sharded.DistributedH)
+    def dist_h_init(self, log2n, n_peers, me):
+        """-> uint8[192]: the IPC handles of this rank's a / b / c slices"""
+        h = np.zeros(192, dtype=np.uint8)
+        _check(load().b200g16_dist_h_init(self.h, log2n, n_peers, me, _ptr(h)))
+        return h
+
+    def dist_h_open(self, all_handles):
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8)
+        _check(load().b200g16_dist_h_open(self.h, _ptr(a)))
+
+    def dist_h_load(self, d_a, d_b, d_c):
+        _check(load().b200g16_dist_h_load(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c))))
+
+    def dist_h_slice(self, which):
+        p = load().b200g16_dist_h_slice(self.h, which)
+        if not p:
+            raise B200Error("dist_h_slice: not initialised")
+        return int(p)
+
+    def dist_h_phase(self, phase):
+        _check(load().b200g16_dist_h_phase(self.h, phase))
+
+    def dist_h_close(self):
+        load().b200g16_dist_h_close(self.h)
 
     # -- MSM (host scalars: numpy (n,4) uint64 Montgomery; or a device pointer + n)
     def msm(self, bases, scalars, offset=0, n=None):

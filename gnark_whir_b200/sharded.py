@@ -206,6 +206,50 @@ def compute_h_distributed(ctx, t_a, t_b, t_c, log2n, pg=None):
     return t_a
 
 
+class DistributedH:
+    """computeH split over the 2 / 4 / 8 ranks of a process group (b200g16_dist_h_*): every rank keeps only its
+    positions [rank M, (rank + 1) M) of a, b, c; the cross-GPU butterfly levels run over CUDA-IPC peer memory, the
+    four phases are separated by barriers, and the rank's slice of h (= its Z shard) stays on its GPU.
+    Bit-identical to b200g16_compute_h_dev (tests/test_gpu_group.py, and the gate of bench.py's sharded prove)."""
+
+    def __init__(self, ctx, log2n, pg=None):
+        import torch.distributed as dist
+        self.ctx, self.L, self.pg = ctx, log2n, pg
+        self.world, self.rank = dist.get_world_size(pg), dist.get_rank(pg)
+        if self.world not in (2, 4, 8):
+            raise ValueError("DistributedH needs 2, 4 or 8 ranks")
+        self.M = (1 << log2n) // self.world
+        mine = ctx.dist_h_init(log2n, self.world, self.rank).tobytes()
+        outs = [None] * self.world
+        dist.all_gather_object(outs, mine, group=pg)       # 192 bytes per rank; works on nccl and gloo groups alike
+        ctx.dist_h_open(np.frombuffer(b"".join(outs), dtype=np.uint8))
+        dist.barrier(group=pg)
+
+    def slice_ptr(self, which):
+        return self.ctx.dist_h_slice(which)
+
+    def load(self, t_a, t_b, t_c):
+        """t_*: torch int64 tensors (M, 4) on this GPU: this rank's zero-padded slices of a, b, c."""
+        import torch
+        for t in (t_a, t_b, t_c):
+            assert t.is_cuda and t.is_contiguous() and t.numel() == 4 * self.M
+        torch.cuda.current_stream().synchronize()          # the slices were produced on torch's stream
+        self.ctx.dist_h_load(t_a.data_ptr(), t_b.data_ptr(), t_c.data_ptr())
+
+    def run(self):
+        """All four phases; returns the device pointer to pass as d_h (so that d_h + 32 off_z is this rank's slice)."""
+        import torch.distributed as dist
+        for phase in range(4):
+            dist.barrier(group=self.pg)
+            self.ctx.dist_h_phase(phase)
+        return self.slice_ptr(0) - 32 * self.rank * self.M
+
+    def close(self):
+        import torch.distributed as dist
+        dist.barrier(group=self.pg)
+        self.ctx.dist_h_close()
+
+
 def prove_distributed(ctx, pk_shard, t_wires, t_a, t_b, t_c, log2n, r, s, device=None, pg=None):
     """One rank's part of a sharded prove with computeH spread over the ranks and overlapped with the
     witness MSMs.  Tensors are torch int64 (n, 4) on this rank's GPU; a, b, c zero-padded, identical on all

@@ -411,6 +411,27 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* pk, const uint
                         const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_constraints,
                         const uint64_t r[4], const uint64_t s[4], b200g16_proof* proof_out, uint64_t* h_out);
 
+/* ---- computeH split over 2 / 4 / 8 GPUs, one PROCESS per GPU ---------------------------------------
+ * (b200g16_group_prove does the same inside one process.)  Rank `me` of n_peers holds positions
+ * [me M, (me + 1) M), M = 2^log2n / n_peers, of a, b, c (zero padded) in three slice buffers owned by the library.
+ * The levels of every transform whose partner lies on another GPU run as kernels over CUDA-IPC mapped peer
+ * memory (NVLink loads / stores, no collective library); all other levels are ordinary size-M passes.
+ *   init   allocates the slices, returns their 3 x 64-byte IPC handles (exchange them: e.g. all_gather)
+ *   open   maps every peer's slices (all_handles = n_peers x 3 x 64 bytes, rank-major)
+ *   load   copies this rank's slices of a, b, c (device pointers, M elements each) into the slice buffers
+ *   slice  device pointer of the local slice of a (0), b (1), c (2) (to write the inputs in place instead)
+ *   phase  runs phase 0..3 on this rank and waits for it; ALL ranks must pass a barrier between consecutive
+ *          phases (and between writing the inputs and phase 0).  After phase 3 slice(0) holds this rank's
+ *          positions of h (bit-reversed order), which is exactly the Z shard of a point-range sharded key:
+ *          pass (char*)slice(0) - 32 * off_z as d_h to b200g16_prove_h_dev / _prove_end_dev.
+ *   close  unmaps and frees. */
+int b200g16_dist_h_init(b200g16_ctx* ctx, unsigned log2n, int n_peers, int me, uint8_t* handles_out);
+int b200g16_dist_h_open(b200g16_ctx* ctx, const uint8_t* all_handles);
+int b200g16_dist_h_load(b200g16_ctx* ctx, const void* d_a, const void* d_b, const void* d_c);
+void* b200g16_dist_h_slice(b200g16_ctx* ctx, int which);
+int b200g16_dist_h_phase(b200g16_ctx* ctx, int phase);
+void b200g16_dist_h_close(b200g16_ctx* ctx);
+
 /* ---- small host-side group helpers (final 8-point reduction of sharded MSMs) ------ */
 /* out = a + b on affine Montgomery points (handles infinity / doubling). Host only. */
 int b200g16_g1_add(const uint64_t a[8], const uint64_t b[8], uint64_t out[8]);

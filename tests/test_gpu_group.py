@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _device_lists():
-    out = [[0], [0, 0], [0, 0, 0], [0] * 5]
+    out = [[0], [0, 0], [0, 0, 0], [0] * 4, [0] * 5, [0] * 8]     # 2 / 4 / 8: computeH split over all devices
     n = torch.cuda.device_count()
     if n >= 2:
         out.append([0, 1])
@@ -82,8 +82,11 @@ def test_group_prove_equals_single_gpu_prove_and_oracle(ctx, devices):
             g.prove(None, f(w), f(a), f(b), f(c), f([r])[0], f([s])[0])
 
 
-def test_group_prove_2p18_known_dlog_key(ctx):
-    """2^18 constraints, window tables, 3 shards: every MSM output, h and the proof against the closed forms."""
+@pytest.mark.parametrize("n_dev", [3, 4, 8])
+def test_group_prove_2p18_known_dlog_key(ctx, n_dev):
+    """2^18 constraints, window tables, 3 shards (a, b, c on three devices, h on the root) and 4 / 8 shards (computeH
+    split over all devices, cross-GPU levels over peer memory): every MSM output, h and the proof against the closed
+    forms."""
     L, N = 18, 1 << 18
     rs = np.random.Generator(np.random.PCG64(1818))
     ks = {"a": synth.rand_fr(rs, N), "b": synth.rand_fr(rs, N), "k": synth.rand_fr(rs, N - 1), "z": synth.rand_fr(rs, N - 1),
@@ -102,7 +105,8 @@ def test_group_prove_2p18_known_dlog_key(ctx):
     key = synth.KnownDlogKey.__new__(synth.KnownDlogKey)
     key.L, key.N, key.k, key.small = L, N, ks, small
     exp, h_exp = key.expected(wires, a, b, c, r, s)
-    devices = [0, 1, 2] if torch.cuda.device_count() >= 3 else [0, 0, 0]
+    nd = torch.cuda.device_count()
+    devices = list(range(n_dev)) if nd >= n_dev else [0] * n_dev
     lib.host_register(wires)                        # the Go shim's b200g16_host_register path
     try:
         with lib.Group(devices) as g:
@@ -116,3 +120,62 @@ def test_group_prove_2p18_known_dlog_key(ctx):
             g.pk_free(pk)
     finally:
         lib.host_unregister(wires)
+
+
+# ---- one PROCESS per rank: the CUDA-IPC path of sharded.DistributedH, two ranks sharing GPU 0 over a gloo group
+def _dist_h_worker(rank, world, port, L, q):
+    import os
+
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = False
+    try:
+        from gnark_whir_b200 import sharded
+        torch.cuda.set_device(0)
+        N = 1 << L
+        M = N // world
+        rs = np.random.Generator(np.random.PCG64(77))                    # same inputs on every rank
+        a, b, c = synth.rand_fr(rs, N), synth.rand_fr(rs, N), synth.rand_fr(rs, N)
+        a[N - 37:] = 0                                                    # zero padding reaches into the last slice
+        want = cport.compute_h(a, b, c, L, 2)
+        with lib.Context(0) as c0:
+            dh = sharded.DistributedH(c0, L)
+            got = []
+            for it in range(2):                                           # twice: buffers and events are reused
+                sl = [torch.from_numpy(v[rank * M:(rank + 1) * M].view(np.int64).copy()).cuda() for v in (a, b, c)]
+                dh.load(*sl)
+                d_h = dh.run()
+                assert d_h + 32 * rank * M == dh.slice_ptr(0)
+                from cuda import cudart
+                host = np.empty((M, 4), dtype=np.uint64)
+                err, = cudart.cudaMemcpy(host.ctypes.data, dh.slice_ptr(0), 32 * M, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+                got.append(int(err) == 0 and np.array_equal(host, want[rank * M:(rank + 1) * M]))
+                dist.barrier()
+            dh.close()
+            ok = all(got)
+    finally:
+        q.put((rank, ok))
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_h_over_cuda_ipc_two_processes(world):
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mctx = mp.get_context("spawn")
+    q = mctx.Queue()
+    procs = [mctx.Process(target=_dist_h_worker, args=(r, world, port, 14, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    assert res == [(r, True) for r in range(world)]
