@@ -93,11 +93,10 @@ struct NttPassArgs {
   int inverse;
 };
 
-// One pass = k radix-2 levels over the index bits [b0, b0 + k) of a tile of 2^k rows x 2^logc columns.  The FIRST
-// level reads its operands straight from global memory (scaled by the coset table when the pass carries one) and
-// the LAST level stores its results straight to global memory (scaled by 1/N or a table): the tile makes k - 1
-// round trips through shared memory instead of k + 1, with k - 1 barriers instead of k + 1, and the global loads
-// of one warp overlap the butterflies of the others instead of forming a phase of their own.
+// (Measured and not kept, profiles/r02c_sweep_ntt_fused_loadstore.jsonl: reading the first level's operands straight
+// from global memory and storing the last level's results straight to it — two shared-memory round trips and two
+// barriers fewer per pass — is 1.4% SLOWER at 2^24 (3.906 vs 3.853 ms): the separate load loop keeps four independent
+// 32-byte loads per thread in flight, the fused form exposes the latency of two.)
 // TFAST: rows contiguous in memory (b0 == 0) -> row index fastest in shared memory.
 template <bool DIT, bool TFAST>
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
@@ -111,9 +110,22 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
   Fr* data = A.nvecs ? A.vecs[blockIdx.y] : A.data + (size_t)blockIdx.y * ((size_t)1 << L);  // batched transforms
   const Fr* post = (A.post_mode == 2 && A.nvecs) ? A.post_vec[blockIdx.y] : A.post;
 
+  // ---- load
+  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+    uint32_t t, c;
+    if (TFAST) { t = x & (rows - 1); c = x >> k; }
+    else { c = x & ((1u << logc) - 1); t = x >> logc; }
+    uint32_t u = (tile << logc) + c;
+    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
+    Fr v = ld_fr(data + i);
+    if (A.pre) v = Fr::mul(v, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i, L) : i)));
+    sm.put(x, v);  // x is exactly the shared-memory slot for this layout
+  }
+  __syncthreads();
+
+  // ---- k radix-2 levels
   const uint32_t nbf = T >> 1;
   for (int step = 0; step < k; step++) {
-    const bool first = step == 0, last = step == k - 1;
     const int lb = DIT ? step : (k - 1 - step);  // local partner bit
     const int pb = b0 + lb;                      // global partner bit
     const uint32_t lbmask = (1u << lb) - 1u;
@@ -121,58 +133,43 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
       uint32_t r, c;
       if (TFAST) { r = q & ((rows >> 1) - 1); c = q >> (k - 1); }
       else { c = q & ((1u << logc) - 1); r = q >> logc; }
-      const uint32_t t0 = ((r >> lb) << (lb + 1)) | (r & lbmask);
-      const uint32_t t1 = t0 | (1u << lb);
-      const uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
-      const uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
-      const uint32_t u = (tile << logc) + c;
-      const uint32_t ibase = ((u >> b0) << (b0 + k)) | (u & lowmask);
-      const uint32_t i0 = ibase | (t0 << b0), i1 = ibase | (t1 << b0);  // global indices of the two operands
-      Fr xv, yv;
-      if (first) {
-        xv = ld_fr(data + i0);
-        yv = ld_fr(data + i1);
-        if (A.pre) {
-          xv = Fr::mul(xv, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i0, L) : i0)));
-          yv = Fr::mul(yv, ldg_fr(A.pre + (A.pre_bitrev ? bitrev_dev(i1, L) : i1)));
-        }
-      } else {
-        xv = sm.get(s0);
-        yv = sm.get(s1);
-      }
-      Fr o0, o1;
+      uint32_t t0 = ((r >> lb) << (lb + 1)) | (r & lbmask);
+      uint32_t t1 = t0 | (1u << lb);
+      uint32_t s0 = TFAST ? ((c << k) | t0) : ((t0 << logc) | c);
+      uint32_t s1 = TFAST ? ((c << k) | t1) : ((t1 << logc) | c);
+      Fr xv = sm.get(s0), yv = sm.get(s1);
       if (pb == 0) {  // the level whose twiddles are all w^0 = 1: no products (warp-uniform branch)
-        o0 = Fr::add(xv, yv);
-        o1 = Fr::sub(xv, yv);
-      } else {
-        const uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
-        const uint32_t e = j << (L - 1 - pb);
-        const Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
-        if (DIT) {
-          yv = Fr::mul(yv, w);
-          o0 = Fr::add(xv, yv);
-          o1 = Fr::sub(xv, yv);
-        } else {
-          o0 = Fr::add(xv, yv);
-          o1 = Fr::mul(Fr::sub(xv, yv), w);
-        }
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::sub(xv, yv));
+        continue;
       }
-      if (last) {
-        if (A.post_mode == 1) {
-          o0 = Fr::mul(o0, A.post_const);
-          o1 = Fr::mul(o1, A.post_const);
-        } else if (A.post_mode == 2) {
-          o0 = Fr::mul(o0, ldg_fr(post + (A.post_bitrev ? bitrev_dev(i0, L) : i0)));
-          o1 = Fr::mul(o1, ldg_fr(post + (A.post_bitrev ? bitrev_dev(i1, L) : i1)));
-        }
-        st_fr(data + i0, o0);
-        st_fr(data + i1, o1);
+      uint32_t u = (tile << logc) + c;
+      uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
+      uint32_t e = j << (L - 1 - pb);
+      Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
+      if (DIT) {
+        yv = Fr::mul(yv, w);
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::sub(xv, yv));
       } else {
-        sm.put(s0, o0);
-        sm.put(s1, o1);
+        sm.put(s0, Fr::add(xv, yv));
+        sm.put(s1, Fr::mul(Fr::sub(xv, yv), w));
       }
     }
-    if (!last) __syncthreads();
+    __syncthreads();
+  }
+
+  // ---- store
+  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+    uint32_t t, c;
+    if (TFAST) { t = x & (rows - 1); c = x >> k; }
+    else { c = x & ((1u << logc) - 1); t = x >> logc; }
+    uint32_t u = (tile << logc) + c;
+    uint32_t i = ((u >> b0) << (b0 + k)) | (t << b0) | (u & lowmask);
+    Fr v = sm.get(x);
+    if (A.post_mode == 1) v = Fr::mul(v, A.post_const);
+    else if (A.post_mode == 2) v = Fr::mul(v, ldg_fr(post + (A.post_bitrev ? bitrev_dev(i, L) : i)));
+    st_fr(data + i, v);
   }
 }
 

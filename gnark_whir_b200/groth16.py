@@ -287,6 +287,100 @@ def vk_read_from(ctx, data, raw=None):
     return vk
 
 
+# ---------------------------------------------------------------- ProvingKey wire format
+ROOT_2_28 = 19103219067921713944291392827692070036145651957329286315305642004821462161904
+
+
+def domain_write_to(log2n, with_precompute=True):
+    """(*fft.Domain).WriteTo (gnark-crypto ecc/bn254/fr/fft/domain.go, as recalled): Cardinality u64 | CardinalityInv |
+    Generator | GeneratorInv | FrMultiplicativeGen | FrMultiplicativeGenInv (fr.Element = 32 bytes big-endian,
+    canonical) | withPrecompute (1 byte)."""
+    n = 1 << log2n
+    gen = pow(ROOT_2_28, 1 << (28 - log2n), R_MOD)
+    vals = [pow(n, -1, R_MOD), gen, pow(gen, -1, R_MOD), 5, pow(5, -1, R_MOD)]
+    return n.to_bytes(8, "big") + b"".join(v.to_bytes(32, "big") for v in vals) + bytes([1 if with_precompute else 0])
+
+
+def domain_read_from(rd):
+    n = int.from_bytes(rd.take(8), "big")
+    vals = [int.from_bytes(rd.take(32), "big") for _ in range(5)]
+    rd.take(1)
+    if n == 0 or n & (n - 1) or n > (1 << 28):
+        raise ValueError("fft.Domain.ReadFrom: cardinality is not a power of two <= 2^28")
+    log2n = n.bit_length() - 1
+    if domain_write_to(log2n)[8:-1] != b"".join(v.to_bytes(32, "big") for v in vals):
+        raise ValueError("fft.Domain.ReadFrom: generator / inverses do not belong to this cardinality")
+    return log2n
+
+
+def pk_write_to(ctx, pk, raw=False):
+    """(*ProvingKey).WriteTo / WriteRawTo (gnark backend/groth16/bn254/marshal.go, as recalled):
+    Domain | G1.Alpha | G1.Beta | G1.Delta | G1.A | G1.B | G1.Z | G1.K | G2.Beta | G2.Delta | G2.B | nbWires u64 |
+    NbInfinityA u64 | NbInfinityB u64 | InfinityA []bool (nbWires bytes, no length) | InfinityB | u32 #commitment keys |
+    per key: pedersen Basis | BasisExpSigma.  Point slices: u32 length + points.  The point encodings run batched on
+    the GPU (b200g16_g1/g2_encode)."""
+    def host(v):
+        return v.download() if hasattr(v, "download") else np.asarray(v, dtype=np.uint64)
+    g1_vecs = [host(v).reshape(-1, 8) for v in (pk.G1_A, pk.G1_B, pk.G1_Z, pk.G1_K)]
+    ped = [host(x).reshape(-1, 8) for ck in pk.CommitmentKeys for x in (ck.Basis, ck.BasisExpSigma)]
+    singles = np.stack([np.asarray(p, dtype=np.uint64).reshape(8) for p in (pk.G1_Alpha, pk.G1_Beta, pk.G1_Delta)])
+    allg1 = np.concatenate([singles] + g1_vecs + ped)
+    e1 = ctx.encode_points(allg1, group=1, raw=raw)
+    g2 = np.concatenate([np.stack([np.asarray(pk.G2_Beta, np.uint64).reshape(16), np.asarray(pk.G2_Delta, np.uint64).reshape(16)]),
+                         host(pk.G2_B).reshape(-1, 16)])
+    e2 = ctx.encode_points(g2, group=2, raw=raw)
+    out = [domain_write_to(pk.log2_domain), e1[0].tobytes(), e1[1].tobytes(), e1[2].tobytes()]
+    o = 3
+    for v in g1_vecs:
+        out += [len(v).to_bytes(4, "big"), e1[o:o + len(v)].tobytes()]
+        o += len(v)
+    out += [e2[0].tobytes(), e2[1].tobytes(), (len(g2) - 2).to_bytes(4, "big"), e2[2:].tobytes()]
+    ia, ib = np.asarray(pk.InfinityA, dtype=np.uint8), np.asarray(pk.InfinityB, dtype=np.uint8)
+    out += [len(ia).to_bytes(8, "big"), int(ia.sum()).to_bytes(8, "big"), int(ib.sum()).to_bytes(8, "big"),
+            (ia != 0).astype(np.uint8).tobytes(), (ib != 0).astype(np.uint8).tobytes(), len(pk.CommitmentKeys).to_bytes(4, "big")]
+    for v in ped:
+        out += [len(v).to_bytes(4, "big"), e1[o:o + len(v)].tobytes()]
+        o += len(v)
+    return b"".join(out)
+
+
+def pk_read_from(ctx, data, k_skip=None):
+    """(*ProvingKey).ReadFrom -> ProvingKey (compressed or raw stream, per-point flag bits).  A compressed key costs one
+    square root per point: decoded in GPU batches.  k_skip (public + committed + commitment wires; gnark derives it from
+    the constraint system at prove time, it is not part of the key) may be given here or set on the result later."""
+    rd = _PointReader(data, "groth16.ProvingKey.ReadFrom")
+    log2n = domain_read_from(rd)
+
+    def vec(group):
+        n = rd.u32()
+        if n > (len(rd.data) - rd.o) // 32:
+            raise ValueError("groth16.ProvingKey.ReadFrom: short buffer")
+        return [rd.point(group) for _ in range(n)]
+    alpha, beta, delta = rd.point(1), rd.point(1), rd.point(1)
+    A, B, Z, K = vec(1), vec(1), vec(1), vec(1)
+    beta2, delta2 = rd.point(2), rd.point(2)
+    B2 = vec(2)
+    nb_wires = int.from_bytes(rd.take(8), "big")
+    nia, nib = int.from_bytes(rd.take(8), "big"), int.from_bytes(rd.take(8), "big")
+    if 2 * nb_wires > len(rd.data) - rd.o:
+        raise ValueError("groth16.ProvingKey.ReadFrom: short buffer")
+    ia = np.frombuffer(rd.take(nb_wires), dtype=np.uint8).copy()
+    ib = np.frombuffer(rd.take(nb_wires), dtype=np.uint8).copy()
+    if int((ia != 0).sum()) != nia or int((ib != 0).sum()) != nib or len(A) != nb_wires - nia or len(B) != nb_wires - nib or len(B2) != len(B):
+        raise ValueError("groth16.ProvingKey.ReadFrom: infinity flags do not match the point vectors")
+    if len(Z) + 1 != (1 << log2n):
+        raise ValueError("groth16.ProvingKey.ReadFrom: len(G1.Z) != N - 1")
+    cks = [(vec(1), vec(1)) for _ in range(rd.u32())]
+    p = rd.decode(ctx)
+
+    def arr(idx, w):
+        return np.stack([p[i] for i in idx]) if idx else np.zeros((0, w), dtype=np.uint64)
+    pk = ProvingKey(log2n, p[alpha], p[beta], p[delta], arr(A, 8), arr(B, 8), arr(Z, 8), arr(K, 8), p[beta2], p[delta2],
+                    arr(B2, 16), ia, ib, None if k_skip is None else np.asarray(k_skip, dtype=np.uint8),
+                    [PedersenProvingKey(arr(b, 8), arr(bs, 8)) for b, bs in cks])
+    return pk
+
+
 @dataclass
 class ToxicWaste:
     tau: int

@@ -195,3 +195,30 @@ def vk_write(alpha1, beta1, beta2, gamma2, delta1, delta2, K, committed_groups, 
     for g, gs in pedersen_keys:
         out += e2(g) + e2(gs)
     return out
+
+
+# ---------------------------------------------------------------- fft.Domain and groth16 ProvingKey
+def domain_write(domain):
+    """(*fft.Domain).WriteTo as recalled: Cardinality u64 | CardinalityInv | Generator | GeneratorInv |
+    FrMultiplicativeGen | FrMultiplicativeGenInv (32-byte big-endian canonical) | withPrecompute (1 byte = 1)."""
+    vals = [domain.card_inv, domain.gen, domain.gen_inv, domain.shift, domain.shift_inv]
+    return domain.n.to_bytes(8, "big") + b"".join(int(v).to_bytes(32, "big") for v in vals) + b"\x01"
+
+
+def pk_write(pk, raw=False):
+    """(*ProvingKey).WriteTo / WriteRawTo as recalled (see gnark_whir_b200/groth16.py pk_write_to) for an
+    oracle.groth16.ProvingKey."""
+    e1, e2 = (g1_raw_bytes, g2_raw_bytes) if raw else (g1_bytes, g2_bytes)
+
+    def sl(points, enc):
+        return len(points).to_bytes(4, "big") + b"".join(enc(q) for q in points)
+    out = domain_write(pk.domain) + e1(pk.alpha1) + e1(pk.beta1) + e1(pk.delta1)
+    out += sl(pk.A, e1) + sl(pk.B, e1) + sl(pk.Z, e1) + sl(pk.K, e1) + e2(pk.beta2) + e2(pk.delta2) + sl(pk.B2, e2)
+    n = len(pk.infinity_a)
+    out += n.to_bytes(8, "big") + sum(pk.infinity_a).to_bytes(8, "big") + sum(pk.infinity_b).to_bytes(8, "big")
+    out += bytes(1 if x else 0 for x in pk.infinity_a) + bytes(1 if x else 0 for x in pk.infinity_b)
+    has = 1 if pk.ped_basis else 0
+    out += has.to_bytes(4, "big")
+    if has:
+        out += sl(pk.ped_basis, e1) + sl(pk.ped_basis_exp_sigma, e1)
+    return out

@@ -146,3 +146,41 @@ def test_verifying_key_wire_format(ctx, raw, with_commitment):
             g16.vk_read_from(ctx, data[:-3], raw=raw)
     finally:
         pk.free()
+
+
+@pytest.mark.parametrize("with_commitment", [False, True])
+@pytest.mark.parametrize("raw", [False, True])
+def test_proving_key_wire_format(ctx, raw, with_commitment):
+    """Setup's pk through pk_write_to: byte-exact with the oracle's layout of (*ProvingKey).WriteTo / WriteRawTo, and
+    pk_read_from gives back a key that proves identically (batched GPU decode: one square root per compressed point)."""
+    from oracle import groth16 as og
+    rng = random.Random(59 + raw)
+    r1cs, w = og.synthetic_r1cs(40, 3, rng, with_commitment=with_commitment)
+    tw = og.ToxicWaste(*[rng.randrange(1, R) for _ in range(5)], sigma=rng.randrange(1, R))
+    pk, vk = g16.Setup(ctx, r1cs, g16.ToxicWaste(tw.tau, tw.alpha, tw.beta, tw.gamma, tw.delta, tw.sigma))
+    opk, _ = og.setup(r1cs, tw)
+    try:
+        data = g16.pk_write_to(ctx, pk, raw=raw)
+        assert data == ser.pk_write(opk, raw=raw)
+        back = g16.pk_read_from(ctx, data, k_skip=pk.k_skip)
+        for f in ("G1_Alpha", "G1_Beta", "G1_Delta", "G1_A", "G1_B", "G1_Z", "G1_K", "G2_Beta", "G2_Delta", "G2_B", "InfinityA", "InfinityB"):
+            assert np.array_equal(np.asarray(getattr(back, f)), np.asarray(getattr(pk, f))), f
+        assert back.log2_domain == pk.log2_domain and len(back.CommitmentKeys) == len(pk.CommitmentKeys)
+        if with_commitment:
+            assert np.array_equal(back.CommitmentKeys[0].Basis, pk.CommitmentKeys[0].Basis)
+            assert np.array_equal(back.CommitmentKeys[0].BasisExpSigma, pk.CommitmentKeys[0].BasisExpSigma)
+        for cut in (7, 8 + 5 * 32, len(data) - 1):            # truncated streams are errors, never a partial key
+            with pytest.raises(ValueError):
+                g16.pk_read_from(ctx, data[:cut])
+        bad = bytearray(data)
+        bad[3] ^= 1                                            # cardinality no longer a power of two
+        with pytest.raises(ValueError):
+            g16.pk_read_from(ctx, bytes(bad))
+        if not with_commitment:                                # the re-read key proves bit-identically
+            r, s_ = rng.randrange(R), rng.randrange(R)
+            p0 = g16.Prove(ctx, r1cs, pk, list(w), r=r, s=s_)
+            p1 = g16.Prove(ctx, r1cs, back, list(w), r=r, s=s_)
+            assert np.array_equal(p0.Ar, p1.Ar) and np.array_equal(p0.Bs, p1.Bs) and np.array_equal(p0.Krs, p1.Krs)
+    finally:
+        pk.free()
+        back.free() if "back" in dir() else None
