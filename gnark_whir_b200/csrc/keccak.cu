@@ -262,6 +262,105 @@ __global__ void __launch_bounds__(128) k_merkle_paths(const uint8_t* __restrict_
                 cur[2] == expected_root[2] && cur[3] == expected_root[3];
 }
 
+// ---- the same path recompute for SMALL batches (one WHIR round opens 64..256 paths): one WARP per path.
+// A path is 24 dependent permutations; one thread runs them in ~8 us each, so a round's paths take 0.2 ms however
+// few they are.  Here lane l = x + 5y of a warp holds state lane A[x, y] (lanes 25..31 idle) and a round is four
+// shuffle stages: theta's column parities (4 independent 64-bit shuffles) and D (2), rho + pi as ONE permuting
+// shuffle of the rotated lane, chi (2) — about 130 cycles of latency per round instead of ~650.
+struct KeccakLaneCtx {
+  int l5, l10, l15, l20;   // lanes of the same column (theta parities)
+  int xm1, xp1;            // a lane of column x-1 / x+1 (theta's D)
+  int pi_src;              // lane whose rotated value lands here (rho + pi)
+  int rot;                 // rho rotation of THIS lane's value before it leaves
+  int c1, c2;              // lanes (x+1, y), (x+2, y) (chi)
+};
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ KeccakLaneCtx keccak_lane_ctx(int lane) {
+  // rho offsets by lane index x + 5y (FIPS-202 table 2)
+  const int kRot[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  KeccakLaneCtx c;
+  const int l = lane < 25 ? lane : 0, x = l % 5, y = l / 5;
+  c.l5 = (l + 5) % 25; c.l10 = (l + 10) % 25; c.l15 = (l + 15) % 25; c.l20 = (l + 20) % 25;
+  c.xm1 = (x + 4) % 5 + 5 * y; c.xp1 = (x + 1) % 5 + 5 * y;
+  c.c1 = (x + 1) % 5 + 5 * y; c.c2 = (x + 2) % 5 + 5 * y;
+  c.rot = kRot[l];
+  // pi: B[y', 2x' + 3y'] = A[x', y'];  this lane (x, y) receives from the (x', y') with y' = x, 2x' + 3y' = y (mod 5)
+  const int yp = x, xp = ((y - 3 * yp) % 5 + 5) * 3 % 5;   // 2^-1 = 3 (mod 5)
+  c.pi_src = xp + 5 * yp;
+  return c;
+}
+
+__device__ __forceinline__ uint64_t keccak_f1600_warp(uint64_t a, const KeccakLaneCtx& c, int lane) {
+#pragma unroll 1
+  for (int rnd = 0; rnd < 24; rnd++) {
+    // theta
+    const uint64_t col = a ^ shfl64(a, c.l5) ^ shfl64(a, c.l10) ^ shfl64(a, c.l15) ^ shfl64(a, c.l20);
+    const uint64_t cm = shfl64(col, c.xm1), cp = shfl64(col, c.xp1);
+    a ^= cm ^ ((cp << 1) | (cp >> 63));
+    // rho (rotate own value) + pi (one permuting shuffle)
+    const uint64_t r = c.rot ? ((a << c.rot) | (a >> (64 - c.rot))) : a;
+    const uint64_t b = shfl64(r, c.pi_src);
+    // chi
+    const uint64_t b1 = shfl64(b, c.c1), b2 = shfl64(b, c.c2);
+    a = b ^ (~b1 & b2);
+    if (lane == 0) a ^= kRC[rnd];
+  }
+  return a;
+}
+
+constexpr int KM_WARPS = 4;
+constexpr size_t MERKLE_WARP_MAX = 8192;   // up to here a warp per path fits the machine in one wave (148 SMs x 64 warps)
+__global__ void __launch_bounds__(32 * KM_WARPS) k_merkle_paths_warp(const uint8_t* __restrict__ leaves, size_t leaf_len,
+                                                                      const uint64_t* __restrict__ leaf_siblings,
+                                                                      const uint64_t* __restrict__ auth_paths,
+                                                                      const uint64_t* __restrict__ indexes, unsigned height,
+                                                                      size_t n, const uint64_t* __restrict__ expected_root,
+                                                                      uint64_t* __restrict__ roots_out,
+                                                                      uint8_t* __restrict__ ok_out) {
+  const int lane = threadIdx.x & 31;
+  const size_t i = (size_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5);
+  if (i >= n) return;   // whole warps leave together
+  const KeccakLaneCtx c = keccak_lane_ctx(lane);
+  // leaf: Absorb(leaf) block by block (overwrite the rate lanes, permute when more data follows), then the permutation
+  // at the head of Squeeze.  leaf_len is a positive multiple of 8 (checked by the entry point).
+  uint64_t a = 0;
+  const uint64_t* leaf = reinterpret_cast<const uint64_t*>(leaves + i * leaf_len);
+  const size_t words = leaf_len / 8;
+  size_t off = 0;
+  while (words - off > (size_t)KECCAK_RATE_LANES) {
+    if (lane < KECCAK_RATE_LANES) a = leaf[off + lane];
+    a = keccak_f1600_warp(a, c, lane);
+    off += KECCAK_RATE_LANES;
+  }
+  if ((size_t)lane < words - off) a = leaf[off + lane];
+  a = keccak_f1600_warp(a, c, lane);
+  const uint64_t idx = indexes[i];
+  const uint64_t* ap = auth_paths + i * (size_t)(height - 1) * 4;
+  for (unsigned level = 0; level < height; level++) {
+    const uint64_t* sp = level == 0 ? leaf_siblings + i * 4 : ap + (size_t)(level - 1) * 4;
+    const bool right = (idx >> level) & 1;       // set bit: current node is the right child
+    const uint64_t cur = shfl64(a, lane & 3);    // lanes 0..7 see cur[lane & 3]
+    uint64_t v = 0;
+    if (lane < 8) {
+      const uint64_t sib = sp[lane & 3];
+      v = ((lane < 4) == right) ? sib : cur;     // left half = sibling iff we are the right child
+    }
+    a = keccak_f1600_warp(v, c, lane);
+  }
+  if (roots_out && lane < 4) roots_out[i * 4 + lane] = a;
+  if (ok_out) {
+    const bool eq = lane >= 4 || (expected_root && a == expected_root[lane]);
+    const unsigned all = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) ok_out[i] = (expected_root && all == 0xffffffffu) ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------ host drivers
 int keccak_f_batch_device(b200g16_ctx* ctx, uint64_t* d_states, size_t n) {
   if (n == 0) return 0;
@@ -286,6 +385,13 @@ int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_l
                         const uint64_t* d_auth, const uint64_t* d_idx, unsigned height, size_t n,
                         const uint64_t* d_expected_root, uint64_t* d_roots, uint8_t* d_ok) {
   if (n == 0) return 0;
+  if (n <= MERKLE_WARP_MAX) {   // latency-bound batch (a WHIR round's queries): one warp per path
+    k_merkle_paths_warp<<<(unsigned)((n + KM_WARPS - 1) / KM_WARPS), 32 * KM_WARPS, 0, ctx->stream>>>(
+        d_leaves, leaf_len, d_sib, d_auth, d_idx, height, n, d_expected_root, d_roots, d_ok);
+    ctx->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   k_merkle_paths<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_leaves, leaf_len, d_sib, d_auth, d_idx,
                                                                         height, n, d_expected_root, d_roots, d_ok);
   ctx->launches++;

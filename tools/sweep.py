@@ -44,10 +44,37 @@ def t_ms(fn, reps=3):
     return best
 
 
+def window_sweep(ctx):
+    """Table-mode window width per (shard) size: whole-MSM device time for c = 15..21 at 2^18..2^22 (the per-GPU shard
+    sizes of an 8-way sharded 2^21..2^24 job), uniform scalars.  Feeds msm_pick_table_window."""
+    gen = g16.g1_point(g16.G1_GEN)
+    for logn in (18, 19, 20, 21, 22):
+        n = 1 << logn
+        ks = rand_fr(n)
+        sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+        want = cport.g1_gen_mul(cport.fr_dot(ks, sc.cpu().numpy().view(np.uint64)))
+        for c in range(15, 22):
+            bases = ctx.fixed_base_mul(gen, ks, group=1, resident=True)
+            bases.precompute(c)
+            best, ok = None, True
+            for _ in range(5):
+                ok = ok and bool(np.array_equal(ctx.msm(bases, sc.data_ptr(), n=n), want))
+                ph = ctx.last_timings()
+                if best is None or sum(ph) < sum(best):
+                    best = ph
+            emit(config="msm_table_window", log2n=logn, window_bits=c, adds_per_point=ctx.msm_plan(bases, n)[1],
+                 device_ms=round(sum(best), 3), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
+            bases.free()
+
+
 def main():
     global TMAD_PEAK
     big = "--big" in sys.argv
     ctx = lib.Context(0)
+    if "--windows" in sys.argv:
+        window_sweep(ctx)
+        ctx.close()
+        return
     rate, _ = ctx.modmul_probe(8, 4, 2000)
     TMAD_PEAK = rate * 136 / 1e12
     emit(probe="modmul", Gmodmul_s=round(rate / 1e9, 2), TMAD_s=round(TMAD_PEAK, 3))
