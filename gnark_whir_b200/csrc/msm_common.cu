@@ -40,13 +40,19 @@ int msm_pick_window(size_t n) {
 }
 
 int msm_pick_table_window(size_t n) {
+  // Measured on B200 with the tree reduction (profiles/r02f_window_sweep.jsonl: whole-MSM device time, uniform
+  // scalars, c = 15..22): 2^18: c = 17 (1.35 ms);  2^19: c = 19 / 20 tie (2.14);  2^20: c = 20 (3.24 against 3.46 at
+  // 19);  2^21: 20 (5.41 / 6.17);  2^22: 20 (9.96 / 11.6);  2^24: 20 (37.7; c = 22 saves 3 ms of additions and loses 4
+  // in the sort and the reduction).  Widths whose TOP window holds only a few scalar bits (c = 18, 19, 21: 2 / 7 / 2
+  // bits) pile every point's top digit into a handful of low buckets of the shared bucket set and pay for it in the
+  // histogram, the scatter and the merge — c = 20 (14 top bits) and c = 17 (16) do not.
+  auto fits = [&](int c) { return (double)n * msm_num_windows(c) < 2.0e9; };
+  if (n >= ((size_t)3 << 17) && fits(20)) return 20;
   int best = 8;
   double best_cost = 1e300;
-  // measured on B200 (gpurun_out probe7: 2^16..2^24): c = 20 at n >= 2^22, 19 at 2^20, 17 at 2^18; beyond
-  // c = 21 the single bucket set's scatter targets (4 W n bytes) stop fitting the L2 window by window
-  for (int c = 8; c <= 21; c++) {
+  for (int c = 8; c <= 17; c++) {
     const int W = msm_num_windows(c);
-    if ((double)n * W >= 2.0e9) continue;
+    if (!fits(c)) continue;
     double cost = (double)W * (double)n + 4.0 * (double)(1u << (c - 1));
     if (cost < best_cost) { best_cost = cost; best = c; }
   }
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ coun
   uint32_t o = task_off[b];
   for (uint32_t t = 0; t < nt; t++) task_bucket[o + t] = b;
   if (nt > 1) atomicMax(&totals[5], nt);  // deepest merge tree needed (k_merge_pass)
+  if (nt > 4) totals[16 + atomicAdd(&totals[2], 1u)] = b;  // more than one first-level sum: finished by k_merge_heavy
 }
 
 

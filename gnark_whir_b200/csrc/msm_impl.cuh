@@ -182,6 +182,79 @@ __global__ void __launch_bounds__(32) k_reduce_weights(const XYZZ<F>* __restrict
   terms[g] = v;
 }
 
+// The END of the tree in one CTA per window: once a level fits 512 threads (l * 2^(n-l) <= 512) the remaining
+// levels, the 2^m weights and the final sum of the n + 1 terms run back to back inside one kernel, separated by
+// __syncthreads instead of launches (12 launches of ~12 us each for one dependent addition, the weights and three
+// sum passes before: profiles/r02f_ncu_launches_bench_2p24.csv).
+constexpr uint32_t REDUCE_TAIL_THREADS = 512;   // <= 128 registers per thread: the XYZZ addition keeps ~95 live
+
+template <class F>
+__global__ void __launch_bounds__(REDUCE_TAIL_THREADS) k_reduce_tail(XYZZ<F>* __restrict__ A, uint32_t nbw, uint32_t n,
+                                                                       uint32_t l0, XYZZ<F>* __restrict__ out) {
+  XYZZ<F>* base = A + (size_t)blockIdx.x * nbw;
+  const uint32_t t = threadIdx.x;
+  for (uint32_t l = l0; l <= n; l++) {
+    const uint32_t s = nbw >> l;
+    if (t < l * s) {
+      const uint32_t j = t / s, i = t % s;
+      XYZZ<F>* p = base + (j ? (nbw >> j) : 0u) + i;
+      XYZZ<F> a = p[0];
+      a.add(p[s]);
+      p[0] = a;
+    }
+    __syncthreads();
+  }
+  // base[0] = G, base[2^m] = U_m.  Scale in place (2^m positions are distinct; position 1 = U_0 needs no doubling),
+  // then sum the n + 1 terms {base[0], base[1], base[2], base[4], ...} by a halving tree over their list index.
+  if (t >= 1 && t < n) {
+    XYZZ<F> v = base[1u << t];
+    for (uint32_t k = 0; k < t; k++) v.dbl();
+    base[1u << t] = v;
+  }
+  __syncthreads();
+  auto slot = [&](uint32_t idx) -> XYZZ<F>* { return base + (idx == 0 ? 0u : (1u << (idx - 1))); };  // term idx of n + 1
+  for (uint32_t len = n + 1; len > 1;) {
+    const uint32_t half = (len + 1) >> 1;
+    if (t < len - half) {
+      XYZZ<F> a = *slot(t);
+      a.add(*slot(t + half));
+      *slot(t) = a;
+    }
+    __syncthreads();
+    len = half;
+  }
+  if (t == 0) out[blockIdx.x] = base[0];
+}
+
+// Buckets split into MORE than MERGE_FANIN tasks (k_tasks lists them: 0/1-heavy witnesses, the low buckets a narrow
+// top window piles its digits into): one CTA per listed bucket finishes the merge as a halving tree over the
+// first-level sums (every MERGE_FANIN-th partial), instead of log4(#tasks) grid-wide launches that find nothing to do
+// for every other bucket.  Grid-stride over the list; totals[2] = list length.
+template <class F>
+__global__ void __launch_bounds__(256) k_merge_heavy(XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ heavy,
+                                                      const uint32_t* __restrict__ counts,
+                                                      const uint32_t* __restrict__ task_off,
+                                                      const uint32_t* __restrict__ totals) {
+  const uint32_t nheavy = totals[2], seg = totals[4];
+  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    const uint32_t b = heavy[h];
+    XYZZ<F>* p = partials + task_off[b];
+    const uint32_t nt = (counts[b] + seg - 1) / seg;
+    uint32_t m = (nt + MERGE_FANIN - 1) / MERGE_FANIN;   // first-level sums sit at p[MERGE_FANIN * i], i < m
+    while (m > 1) {
+      const uint32_t half = (m + 1) >> 1;
+      for (uint32_t i = threadIdx.x; i < m - half; i += blockDim.x) {
+        XYZZ<F> a = p[(size_t)MERGE_FANIN * i];
+        a.add(p[(size_t)MERGE_FANIN * (i + half)]);
+        p[(size_t)MERGE_FANIN * i] = a;
+      }
+      __syncthreads();
+      m = half;
+    }
+    __syncthreads();
+  }
+}
+
 // plain sums, fan-in 4: out[w][g] = sum_{j<4} in[w][4 g + j]   (len_in items per window, thread per g);
 // applied until one item per window is left (3 dependent additions per level)
 constexpr uint32_t SUM_FANIN = 4;
@@ -277,6 +350,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   uint32_t* entries = ws.entries.as<uint32_t>();
   uint32_t* task_bucket = ws.tasks[spar].as<uint32_t>();
   uint32_t* task_order = task_bucket + max_tasks;
+  uint32_t* heavy = totals + 16;   // list of buckets split into more than MERGE_FANIN tasks (k_tasks), nb entries reserved
   XYZZ<F>* partials = ws.partials[par].as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks[par].as<XYZZ<F>>();
   XYZZ<F>* windows = nullptr;
@@ -316,27 +390,22 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   // dependency chains), so that the next MSM's sort + accumulate on `st` overlap it
   B200_CUDA(cudaEventRecord(ctx->ev_front[par], st));
   B200_CUDA(cudaStreamWaitEvent(tail, ctx->ev_front[par], 0));
-  int merge_levels = 0;
-  for (uint64_t stride = 1; stride < max_tasks; stride *= MERGE_FANIN, merge_levels++)
-    k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, tail>>>(partials, task_bucket, counts, task_off, totals,
-                                                             (uint32_t)stride);
+  // split buckets: one grid-wide fan-in-4 pass, then one CTA per bucket that still has more than one first-level sum
+  k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, tail>>>(partials, task_bucket, counts, task_off, totals, 1u);
+  k_merge_heavy<F><<<(unsigned)ctx->sm_count * 2, 256, 0, tail>>>(partials, heavy, counts, task_off, totals);
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
   const uint32_t nlev = (uint32_t)cfg.c - 1;  // log2(buckets per window)
+  uint32_t l0 = 1;                            // first level the one-CTA tail kernel can take
+  while (l0 <= nlev && (uint64_t)l0 * (cfg.nbw >> l0) > REDUCE_TAIL_THREADS) l0++;
+  if (l0 < 2) l0 = 2;                         // level 1 (reads the partials through the task table) is always its own kernel
   k_reduce_first<F><<<cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128), 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr,
                                                                                  cfg.nbw, chunks);
-  for (uint32_t l = 2; l <= nlev; l++)
+  int sum_levels = 2;
+  for (uint32_t l = 2; l < l0 && l <= nlev; l++, sum_levels++)
     k_reduce_level<F><<<cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), 128), 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
-  // 2^m U_m and G -> nlev + 1 terms per window, then plain fan-in-4 sums: ping-pong between two rows behind the tree
-  XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;
-  XYZZ<F>* nxt = cur + (size_t)cfg.Wr * (nlev + 1);
-  k_reduce_weights<F><<<cdiv((size_t)cfg.Wr * (nlev + 1), 32), 32, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, nlev, cur);
-  int sum_levels = (int)nlev + 1;  // counted as launches below
-  for (uint32_t len = nlev + 1; len > 1; sum_levels++) {
-    const uint32_t len_out = (len + SUM_FANIN - 1) / SUM_FANIN, total_out = (uint32_t)cfg.Wr * len_out;
-    k_sum_pass<F><<<cdiv(total_out, 128), 128, 0, tail>>>(cur, len, len_out, total_out, nxt);
-    XYZZ<F>* t = cur; cur = nxt; nxt = t;
-    len = len_out;
-  }
+  XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;   // Wr window sums behind the tree
+  k_reduce_tail<F><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
+  const int merge_levels = 2;
   windows = cur;  // Wr items
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
   ctx->launches += merge_levels + sum_levels;

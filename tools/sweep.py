@@ -48,12 +48,12 @@ def window_sweep(ctx):
     """Table-mode window width per (shard) size: whole-MSM device time for c = 15..21 at 2^18..2^22 (the per-GPU shard
     sizes of an 8-way sharded 2^21..2^24 job), uniform scalars.  Feeds msm_pick_table_window."""
     gen = g16.g1_point(g16.G1_GEN)
-    for logn in (18, 19, 20, 21, 22):
+    for logn in (18, 19, 20, 21, 22, 24):
         n = 1 << logn
         ks = rand_fr(n)
         sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
         want = cport.g1_gen_mul(cport.fr_dot(ks, sc.cpu().numpy().view(np.uint64)))
-        for c in range(15, 22):
+        for c in (range(15, 22) if logn < 24 else (20, 21, 22)):
             bases = ctx.fixed_base_mul(gen, ks, group=1, resident=True)
             bases.precompute(c)
             best, ok = None, True
