@@ -598,6 +598,26 @@ def extras_single_gpu(ctx, D, st, args):
                             "GBs_400B": round(400 * nk / ms / 1e6, 1)}
     del stt
     torch.cuda.empty_cache()
+    # the same MSM WITHOUT the window table (the table costs 13x the key's HBM): resident scalars, 3 steps
+    try:
+        from oracle import cport, synth
+        rs2 = np.random.Generator(np.random.PCG64(SEED + 3))
+        n2 = 1 << args.logn
+        ks2 = rand_fr(rs2, n2)
+        plain = ctx.fixed_base_mul(synth.G1, ks2, group=1, resident=True)
+        sc2 = rand_fr(rs2, n2)
+        d_sc2 = torch.from_numpy(sc2.view(np.int64)).to(dev)
+        got = ctx.msm(plain, d_sc2.data_ptr(), n=n2)
+        ok = bool(np.array_equal(got, cport.g1_gen_mul(cport.fr_dot(ks2, sc2, host_threads()))))
+        ms = t_ms(lambda: ctx.msm(plain, d_sc2.data_ptr(), n=n2))
+        c2, w2 = ctx.msm_plan(plain, n2)
+        ex["msm_no_table"] = {"log2n": args.logn, "ms": round(ms, 3), "Mpts_s": round(n2 / ms / 1e3, 2), "window_bits": c2,
+                              "adds_per_point": w2, "result_checked_vs_oracle": ok}
+        plain.free()
+        del d_sc2
+        torch.cuda.empty_cache()
+    except Exception as e:
+        ex["msm_no_table"] = {"error": repr(e)}
     ex["groth16_prove"] = []
     for Lp in args.prove_logns:
         try:

@@ -9,6 +9,14 @@
 // carry chains over 64-bit-aligned column pairs ("even"/"odd" accumulators) so that every
 // 32x32 partial product is one mad.lo.cc/madc.hi.cc pair (one IMAD.WIDE on sm_100a) and no
 // partial product ever needs a separate carry fix-up: 2*8*8 + 8 = 136 multiply-adds.
+//
+// Lineage: the even/odd word-serial scheme and its helper structure (mul_n, cmad_n, madc_n_rshift,
+// mad_n_redc, the final "even[i] + odd[i+1]" hand-over) are the published technique of Supranational's
+// sppark (mont_t.cuh), which ICICLE's field code also follows; it is the natural mapping of a Montgomery
+// product onto mad.lo.cc / madc.hi.cc and is restated here, not copied from the reference (which contains
+// no GPU code).  Original to this file: the dedicated square (sqr_ptx), the fused two-term product
+// (dot2_ptx), and the bit-exact host emulation the CPU test-suite pins them with.  fp52.cuh holds the
+// measured alternative on the FP64 pipe (no faster on B200: DESIGN.md §2).
 #pragma once
 #include "bn254_constants.h"
 #include "ptx.cuh"

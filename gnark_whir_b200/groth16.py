@@ -10,7 +10,10 @@ restated.  What runs where:
   Prove   host: the constraint "solver" (here: L.w, R.w, O.w from a full assignment), the BSB22
                 challenge hash, sampling r, s
           GPU : Pedersen commit + PoK (b200g16_msm_g1), computeH, the five MSMs, via b200g16_prove
-  Verify  not built yet; tests verify proofs with the oracle's pairing.
+  Verify  host: the BSB22 challenge hash
+          GPU : public-input MSM, Pedersen PoK check and the pairing product, via b200g16_verify
+  wire formats (gnark / gnark-crypto marshal.go): Proof, VerifyingKey, ProvingKey, fft.Domain; the point encodings run
+          batched on the GPU (b200g16_g1/g2_encode / _decode)
 
 The host language would be Go (a cgo shim) if a Go toolchain existed in this
 image; this module is the same marshalling in Python over ctypes.  There is no CPU fallback:

@@ -30,7 +30,7 @@ def test_reference_arm_prints_the_contract_line():
 
 
 def test_committed_gpu_bench_lines_carry_every_contract_key():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01*_bench_default.json")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_bench_default.json")))
     assert files, "no committed bench line under profiles/"
     d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "cpu_baseline"} <= set(d)
@@ -43,3 +43,18 @@ def test_committed_gpu_bench_lines_carry_every_contract_key():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if "r02" in os.path.basename(files[-1]):       # round-2 additions to the line
+        assert d["cpu_baseline"]["sample"].count("2^24") and "e2e_pageable" in d and "peak_raw_imad_wide" in d["roofline"]
+        proves = d["extras"]["groth16_prove"]
+        assert [p["log2_constraints"] for p in proves] == [20, 24]
+        for p in proves:
+            assert p["result_checked_vs_oracle"] is True and p["e2e"]["h2d_bytes_per_step"] > 0 and p["cpu_baseline"]["kind"] == "port"
+
+
+def test_reference_arm_for_the_prove_metric():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "prove",
+                          "--prove-logn", "8", "--cpu-prove-logn", "8", "--steps", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
+    assert line["config"]["same_size_as_gpu_arm"] is True and line["cpu_baseline"]["kind"] == "port"
