@@ -280,6 +280,16 @@ int b200g16_set_msm_window(b200g16_ctx* ctx, int c) {
   return 0;
 }
 
+int b200g16_set_msm_batch_affine(b200g16_ctx* ctx, int mode, int levels, unsigned min_pairs) {
+  if (!ctx || mode < 0 || mode > 2 || levels < 0 || levels > AFF_LEVELS_MAX)
+    return fail(B200G16_ERR_ARG, "set_msm_batch_affine: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->msm_affine_mode = mode;
+  if (levels) ctx->msm_affine_levels = levels;
+  if (min_pairs) ctx->msm_affine_min_pairs = min_pairs;
+  return 0;
+}
+
 int b200g16_bases_upload_g1(b200g16_ctx* ctx, const uint64_t* points, size_t n, b200g16_bases** out) {
   return upload<Fp>(ctx, points, n, 1, out);
 }

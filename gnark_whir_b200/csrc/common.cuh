@@ -66,10 +66,15 @@ struct DevBuf {
 
 constexpr int MSM_SETS = 3;  // rotating buffer sets: an MSM only waits for the tail of the MSM three calls back
 
+constexpr int AFF_WS_LEVELS = 4;  // = AFF_LEVELS_MAX of msm_affine.cuh (checked where both are visible)
+
 struct MsmWorkspace {
   // everything the "tail" of an MSM reads (merge of split buckets + bucket reduction) exists MSM_SETS times: the
   // tail runs on a second stream while the next MSMs' sort + accumulate ("front") fill the other sets
   DevBuf scalars, digits, entries, counts[MSM_SETS], partials[MSM_SETS], chunks[MSM_SETS], misc[MSM_SETS], tasks[MSM_SETS];
+  // batched-affine accumulation: level buffers of the pair tree (aff_lvl[l - 1] = inputs of level l), one spill slot per
+  // thread.  One set: accumulate kernels of consecutive MSMs are serialised on the main stream.
+  DevBuf aff_lvl[AFF_WS_LEVELS], aff_desc, aff_spill, aff_spill_task;
   void* pinned = nullptr;  // small host staging for window sums
   size_t pinned_cap = 0;
 };
@@ -157,6 +162,9 @@ struct b200g16_ctx {
   b200::DevBuf io_a, io_b, io_c;  // staging for host-pointer entry points
   b200::Timings timings = {};
   int msm_window_override = 0;  // 0 = auto
+  int msm_affine_mode = 0;      // batched-affine accumulation: 0 = never, 1 = by size, 2 = always
+  int msm_affine_levels = 3;    // pair-tree levels at most (1 .. 4)
+  uint32_t msm_affine_min_pairs = 192;  // additions per inversion below which a level is not worth running
   uint64_t launches = 0;        // kernels launched by this ctx (bench's gpu_launches)
 };
 

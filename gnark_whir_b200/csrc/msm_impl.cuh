@@ -272,7 +272,15 @@ __global__ void __launch_bounds__(128) k_sum_pass(const XYZZ<F>* __restrict__ in
   out[g] = acc;
 }
 
+}  // namespace b200
+#include "msm_affine.cuh"
+namespace b200 {
+static_assert(AFF_WS_LEVELS == AFF_LEVELS_MAX, "workspace holds one buffer per pair-tree level");
+
 // ------------------------------------------------------------------------------ host driver
+// entries (= n * W at most) from which the batched-affine accumulation is used in mode 1
+constexpr size_t AFF_AUTO_MIN_ENTRIES = (size_t)40 << 20;
+
 // Window table attached to a bases vector (b200g16_bases_precompute): row k holds 2^(c k) * P_i, so
 // digit k of scalar i addresses entry k * stride + i and ALL windows accumulate into one bucket set.
 // (struct MsmTable lives in common.cuh)
@@ -383,8 +391,44 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
     ctx->last_sort.valid = false;   // one sharer per sort
     if (record_events) { mark(); mark(); mark(); }
   }
-  k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_order, task_bucket, offsets, counts, task_off,
-                                                         totals, partials);
+  const bool use_aff = ctx->msm_affine_mode == 2 || (ctx->msm_affine_mode == 1 && m_max >= AFF_AUTO_MIN_ENTRIES);
+  if (use_aff) {
+    const char* tune_env = getenv("B200G16_AFF_TUNE");   // experiments only (tools/sweep.py --affine)
+    const uint32_t tune = tune_env ? (uint32_t)strtoul(tune_env, nullptr, 0) : 0x11u;
+    const bool occ4 = sizeof(F) <= 32 && ((tune >> 8) & 1u);
+    const unsigned grid = (unsigned)ctx->sm_count * ((sizeof(F) > 32) ? 2u : (occ4 ? 4u : 3u));   // one wave: equal shares per thread
+    const uint32_t T = grid * 128u;
+    AffArgs<F> A;
+    A.bases = d_bases; A.entries = entries; A.task_bucket = task_bucket; A.offsets = offsets; A.counts = counts;
+    A.task_off = task_off; A.totals = totals; A.partials = partials;
+    A.max_levels = ctx->msm_affine_levels < 1 ? 1 : (ctx->msm_affine_levels > AFF_LEVELS_MAX ? AFF_LEVELS_MAX : ctx->msm_affine_levels);
+    A.min_pairs = ctx->msm_affine_min_pairs;
+    A.tune = tune;
+    A.lvl[0] = nullptr;
+    for (int l = 1; l <= AFF_LEVELS_MAX; l++) {
+      A.lvl[l] = nullptr;
+      if (l > A.max_levels) continue;
+      B200_TRY(ws.aff_lvl[l - 1].ensure(((m_max >> l) + max_tasks + T + 16) * sizeof(Affine<F>)));
+      A.lvl[l] = ws.aff_lvl[l - 1].as<Affine<F>>();
+    }
+    B200_TRY(ws.aff_desc.ensure((max_tasks + T + 16) * sizeof(AffDesc)));
+    A.desc = ws.aff_desc.as<AffDesc>();
+    B200_TRY(ws.aff_spill.ensure((size_t)T * sizeof(XYZZ<F>)));
+    B200_TRY(ws.aff_spill_task.ensure((size_t)T * sizeof(uint32_t)));
+    A.spill = ws.aff_spill.as<XYZZ<F>>();
+    A.spill_task = ws.aff_spill_task.as<uint32_t>();
+    if constexpr (sizeof(F) > 32) {
+      k_accumulate_affine<F, 2><<<grid, 128, 0, st>>>(A);
+    } else {
+      if (occ4) k_accumulate_affine<F, 4><<<grid, 128, 0, st>>>(A);
+      else k_accumulate_affine<F, 3><<<grid, 128, 0, st>>>(A);
+    }
+    k_aff_fixup<F><<<cdiv(T, 128), 128, 0, st>>>(partials, A.spill, A.spill_task, T);
+    ctx->launches += 1;
+  } else {
+    k_accumulate<F><<<cdiv(max_tasks, 128), 128, 0, st>>>(d_bases, entries, task_order, task_bucket, offsets, counts, task_off,
+                                                           totals, partials);
+  }
   mark();
   // ---- tail: merge of split buckets + bucket reduction on the second stream (few active threads, long
   // dependency chains), so that the next MSM's sort + accumulate on `st` overlap it

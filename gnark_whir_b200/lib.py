@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200g16_launch_count": (C.c_uint64, [_vp]),
     "b200g16_last_timings": (C.c_int, [_vp, C.POINTER(C.c_float), C.c_int]),
     "b200g16_set_msm_window": (C.c_int, [_vp, C.c_int]),
+    "b200g16_set_msm_batch_affine": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint]),
     "b200g16_bases_upload_g1": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
     "b200g16_bases_upload_g2": (C.c_int, [_vp, _vp, _sz, C.POINTER(_vp)]),
     "b200g16_bases_free": (None, [_vp]),
@@ -122,6 +123,10 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+# b200g16_set_msm_batch_affine(mode, levels, min_pairs) as a fresh ctx has it
+MSM_BATCH_AFFINE_DEFAULT = (0, 3, 192)
 
 
 def _check(status):
@@ -378,6 +383,10 @@ class Context:
 
     def set_msm_window(self, c):
         _check(load().b200g16_set_msm_window(self.h, int(c)))
+
+    def set_msm_batch_affine(self, mode, levels=0, min_pairs=0):
+        """0 = mixed XYZZ bucket additions, 1 = batched-affine pair tree for large inputs, 2 = always."""
+        _check(load().b200g16_set_msm_batch_affine(self.h, int(mode), int(levels), int(min_pairs)))
 
     # -- bases
     def upload_g1(self, points):

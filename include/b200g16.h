@@ -115,6 +115,11 @@ uint64_t b200g16_launch_count(const b200g16_ctx* ctx);
 int b200g16_last_timings(const b200g16_ctx* ctx, float* out_ms, int cap);
 /* Force the Pippenger window width (0 = automatic). Testing / tuning only. */
 int b200g16_set_msm_window(b200g16_ctx* ctx, int c);
+/* Bucket accumulation by BATCHED-AFFINE additions (gnark-crypto's processChunkG1BatchAffine counterpart,
+ * ecc/bn254/multiexp_affine.go; csrc/msm_affine.cuh): mode 0 = never (mixed XYZZ additions), 1 = for large inputs,
+ * 2 = always.  levels = pair-tree levels at most (1..4, 0 keeps the current value), min_pairs = additions per
+ * inversion below which a level is not run (0 keeps the current value).  The MSM result is bit-identical. */
+int b200g16_set_msm_batch_affine(b200g16_ctx* ctx, int mode, int levels, unsigned min_pairs);
 
 /* ---- resident bases (the proving key's point vectors) ---------------------------- */
 /* Copies n affine points to the GPU once; replaces the lazy device copy gnark's icicle

@@ -261,3 +261,68 @@ def test_concurrent_calls_on_one_context(ctx, rng):
     for g, e in zip(got, expect):
         assert np.array_equal(g, e)
     assert len({e.tobytes() for e in expect}) == len(expect)
+
+
+# ---- batched-affine bucket accumulation (csrc/msm_affine.cuh; gnark-crypto multiexp_affine.go counterpart): forced on,
+# every pair-tree level allowed from one pair per inversion up, so that inputs the oracle finishes in seconds walk
+# through levels, odd leftovers, one-element pieces, shares cut in the middle of a task and the spill fix-up.
+@pytest.fixture
+def affine_ctx(ctx):
+    ctx.set_msm_batch_affine(2, 4, 1)
+    yield ctx
+    ctx.set_msm_batch_affine(*lib_defaults())
+
+
+def lib_defaults():
+    from gnark_whir_b200 import lib
+    return lib.MSM_BATCH_AFFINE_DEFAULT
+
+
+@pytest.mark.parametrize("mix", ["uniform", "whir"])
+@pytest.mark.parametrize("logn,levels", [(10, 4), (15, 1), (15, 4), (16, 2), (16, 3), (17, 4)])
+def test_msm_g1_batch_affine_known_dlog(affine_ctx, rng, logn, levels, mix):
+    affine_ctx.set_msm_batch_affine(2, levels, 1)
+    out, exp = _known_dlog_case(affine_ctx, rng, 1 << logn, 1, mix)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("mix", ["uniform", "whir"])
+def test_msm_g2_batch_affine_known_dlog(affine_ctx, rng, mix):
+    out, exp = _known_dlog_case(affine_ctx, rng, 1 << 14, 2, mix)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_msm_batch_affine_repeated_bases(affine_ctx, rng, group):
+    """Few distinct bases (one of them infinity) and few distinct scalars incl. s / r - s pairs: the pair tree meets
+    P + P (tangent), P + (-P) (infinity as a result, then as an operand) and infinity inputs at every level."""
+    n = 1 << (15 if group == 1 else 13)
+    kset = [0] + [rng.randrange(1, R) for _ in range(5)]
+    s0 = [rng.randrange(R) for _ in range(3)]
+    sset = s0 + [R - s for s in s0] + [1, R - 1]
+    ks = [kset[rng.randrange(len(kset))] for _ in range(n)]
+    ss = [sset[rng.randrange(len(sset))] for _ in range(n)]
+    gen = bn.g1_to_array([bn.G1_GEN])[0] if group == 1 else bn.g2_to_array([bn.G2_GEN])[0]
+    bases = affine_ctx.fixed_base_mul(gen, bn.fr_to_mont_array(ks), group=group, resident=True)
+    for c in (0, 7):
+        affine_ctx.set_msm_window(c)
+        out = affine_ctx.msm(bases, bn.fr_to_mont_array(ss))
+        affine_ctx.set_msm_window(0)
+        dot = sum(k * s for k, s in zip(ks, ss)) % R
+        exp = bn.g1_to_array([bn.g1_mul(bn.G1_GEN, dot)])[0] if group == 1 else bn.g2_to_array([bn.g2_mul(bn.G2_GEN, dot)])[0]
+        assert np.array_equal(out, exp), c
+    bases.free()
+
+
+def test_msm_g1_batch_affine_heavy_bucket_and_table(affine_ctx, rng):
+    """All scalars 1 (one bucket, tasks longer than a share: several spills per task), then a window table."""
+    n = 1 << 17
+    ks = [rng.randrange(1, R) for _ in range(n)]
+    bases = affine_ctx.fixed_base_mul(bn.g1_to_array([bn.G1_GEN])[0], bn.fr_to_mont_array(ks), group=1, resident=True)
+    out = affine_ctx.msm(bases, bn.fr_to_mont_array([1] * n))
+    assert np.array_equal(out, bn.g1_to_array([bn.g1_mul(bn.G1_GEN, sum(ks) % R)])[0])
+    ss = [rng.randrange(R) for _ in range(n)]
+    exp = bn.g1_to_array([bn.g1_mul(bn.G1_GEN, sum(k * s for k, s in zip(ks, ss)) % R)])[0]
+    bases.precompute(14)
+    assert np.array_equal(affine_ctx.msm(bases, bn.fr_to_mont_array(ss)), exp)
+    bases.free()

@@ -19,6 +19,14 @@ KEYS = [
     ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall_mio_throttle"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg_throttle"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall_no_instruction"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall_branch_resolving"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall_dispatch"),
+    ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "stall_imc_miss"),
+    ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "stall_tex_throttle"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active_threads_per_inst"),
+    ("l1tex__t_sector_hit_rate.pct", "l1_hit%"), ("lts__t_sector_hit_rate.pct", "l2_hit%"),
 ]
 
 

@@ -67,12 +67,115 @@ def window_sweep(ctx):
             bases.free()
 
 
+def affine_sweep(ctx):
+    """Batched-affine bucket accumulation (csrc/msm_affine.cuh) against the mixed XYZZ accumulation on the same sorted
+    lists: G1 2^20..2^24 and G2 2^20..2^22, window tables, uniform and WHIR-shaped scalars, pair-tree levels 1..4."""
+    tbl = torch.from_numpy(g16.fr_array(list(range(256))).view(np.int64)).cuda()
+    args = [a for a in sys.argv if a.startswith("--logs=")]
+    for group, logs in ((1, [20, 22, 24]), (2, [20, 22])):
+        if args:
+            logs = [int(x) for x in args[0][7:].split(",") if (group == 1) == (int(x) > 0)]
+            logs = [abs(x) for x in logs]
+        gen = g16.g1_point(g16.G1_GEN) if group == 1 else g16.g2_point(g16.G2_GEN)
+        for logn in logs:
+            n = 1 << logn
+            ks = rand_fr(n)
+            bases = ctx.fixed_base_mul(gen, ks, group=group, resident=True)
+            bases.precompute(0)
+            d_uni = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+            u = torch.rand(n, device="cuda")
+            sv = torch.randint(0, 256, (n,), device="cuda")
+            d_mix = d_uni.clone()
+            m01, mb = u < 0.4, (u >= 0.4) & (u < 0.7)
+            d_mix[m01] = tbl[sv[m01] & 1]
+            d_mix[mb] = tbl[sv[mb]]
+            for name, d_sc in (("uniform", d_uni), ("whir_mix", d_mix)):
+                host_sc = d_sc.cpu().numpy().view(np.uint64)
+                dot = cport.fr_dot(ks, host_sc)
+                want = cport.g1_gen_mul(dot) if group == 1 else ctx.fixed_base_mul(gen, dot.reshape(1, 4), group=2)[0]
+                for mode, levels in ((0, 0), (2, 1), (2, 2), (2, 3), (2, 4)):
+                    ctx.set_msm_batch_affine(mode, levels, 0)
+                    best, ok = None, True
+                    for _ in range(4):
+                        ok = ok and bool(np.array_equal(ctx.msm(bases, d_sc.data_ptr(), n=n), want))
+                        ph = ctx.last_timings()
+                        if best is None or sum(ph) < sum(best):
+                            best = ph
+                    emit(config="msm_batch_affine", group=f"G{group}", log2n=logn, scalars=name,
+                         accumulate="xyzz" if mode == 0 else f"affine_L{levels}", device_ms=round(sum(best), 3),
+                         accumulate_ms=round(best[2], 3), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
+                ctx.set_msm_batch_affine(0, 0, 0)
+            bases.free()
+            del d_uni, d_mix
+
+
+def affine_tune(ctx):
+    """Prefetch kind / distance / occupancy variants of k_accumulate_affine (B200G16_AFF_TUNE), one size."""
+    import os
+    args = [a for a in sys.argv if a.startswith("--logs=")]
+    logn = int(args[0][7:]) if args else 22
+    lv = [a for a in sys.argv if a.startswith("--levels=")]
+    levels = int(lv[0][9:]) if lv else 2
+    tn = [a for a in sys.argv if a.startswith("--tunes=")]
+    tunes = [int(x, 0) for x in tn[0][8:].split(",")] if tn else [0x00, 0x11, 0x09, 0x06, 0x0a, 0x2a, 0x31]
+    n = 1 << logn
+    ks = rand_fr(n)
+    bases = ctx.fixed_base_mul(g16.g1_point(g16.G1_GEN), ks, group=1, resident=True)
+    bases.precompute(0)
+    d_sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+    want = cport.g1_gen_mul(cport.fr_dot(ks, d_sc.cpu().numpy().view(np.uint64)))
+    ctx.set_msm_batch_affine(2, levels, 0)
+    for occ in (0, 0x100):
+        for tune in tunes:
+            os.environ["B200G16_AFF_TUNE"] = str(tune | occ)
+            best, ok = None, True
+            for _ in range(3):
+                ok = ok and bool(np.array_equal(ctx.msm(bases, d_sc.data_ptr(), n=n), want))
+                ph = ctx.last_timings()
+                if best is None or ph[2] < best[2]:
+                    best = ph
+            emit(config="msm_batch_affine_tune", log2n=logn, levels=levels, tune=hex(tune | occ), accumulate_ms=round(best[2], 3),
+                 bit_exact_vs_oracle=ok)
+    ctx.set_msm_batch_affine(0, 0, 0)
+    bases.free()
+
+
+def affine_debug(ctx):
+    """Batched-affine against XYZZ on the same inputs, small sizes, every level count."""
+    for logn in (8, 10, 12, 14, 15, 16, 17):
+        n = 1 << logn
+        ks = rand_fr(n)
+        bases = ctx.fixed_base_mul(g16.g1_point(g16.G1_GEN), ks, group=1, resident=True)
+        d_sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+        ctx.set_msm_batch_affine(0, 0, 0)
+        want = ctx.msm(bases, d_sc.data_ptr(), n=n)
+        res = {}
+        for name, levels, mp in (("L0", 1, 1 << 30), ("L1", 1, 1), ("L2", 2, 1), ("L3", 3, 1), ("L4", 4, 1)):
+            ctx.set_msm_batch_affine(2, levels, mp)
+            res[name] = bool(np.array_equal(ctx.msm(bases, d_sc.data_ptr(), n=n), want))
+        emit(config="affine_debug", log2n=logn, plan=ctx.msm_plan(bases, n), **res)
+        bases.free()
+    ctx.set_msm_batch_affine(0, 3, 192)
+
+
 def main():
     global TMAD_PEAK
     big = "--big" in sys.argv
     ctx = lib.Context(0)
     if "--windows" in sys.argv:
         window_sweep(ctx)
+        ctx.close()
+        return
+    if "--affine-tune" in sys.argv:
+        affine_tune(ctx)
+        ctx.close()
+        return
+    if "--affine-debug" in sys.argv:
+        affine_debug(ctx)
+        ctx.close()
+        return
+    if "--affine" in sys.argv:
+        affine_sweep(ctx)
         ctx.close()
         return
     rate, _ = ctx.modmul_probe(8, 4, 2000)
