@@ -191,9 +191,15 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
     bool open = false;
     AffDesc nd = D[0];
     for (;;) {
-      if (i >= np) {
+      // piece boundary as an INNER loop (it also skips pieces without a pair): the lanes of a warp reach their
+      // boundaries at different steps, and a `continue` here lets the compiler keep the two paths apart for good —
+      // the warp then runs the body below once per group of lanes (measured: 22.8 of 32 lanes active per instruction,
+      // 30.7 with the inner loop)
+      bool more = true;
+      while (i >= np) {
         if (open && (c & 1)) out[outb + np] = aff_load(A, l, s, inb, c - 1);  // odd element: passes through
-        if (j >= P) break;
+        open = false;
+        if (j >= P) { more = false; break; }
         const AffDesc d = nd;
         const uint32_t tg = t0 + j + g;
         j++;
@@ -205,8 +211,8 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
         inb = ceil_shr(s, l) + tg;
         outb = ceil_shr(s, l + 1) + tg;
         open = true;
-        continue;
       }
+      if (!more) break;
       if (pfk) {
         if (l == 0) {
           const uint32_t pos = s + 2 * i + 2 * PF;
@@ -241,8 +247,9 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
     int32_t i = -1;
     AffDesc nd = D[P - 1];
     for (;;) {
-      if (i < 0) {
-        if (j == 0) break;
+      bool more = true;
+      while (i < 0) {
+        if (j == 0) { more = false; break; }
         const AffDesc d = nd;
         j--;
         const uint32_t tg = t0 + j + g;
@@ -252,8 +259,8 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
         i = (int32_t)np - 1;
         inb = ceil_shr(s, l) + tg;
         outb = ceil_shr(s, l + 1) + tg;
-        continue;
       }
+      if (!more) break;
       if (pfk) {
         if (l == 0) {
           const uint32_t pos = s + 2 * (uint32_t)i;
@@ -309,12 +316,14 @@ B200_HD void aff_thread(const AffArgs<F>& A, uint32_t g, uint32_t T) {
   XYZZ<F> acc = XYZZ<F>::inf();
   AffDesc nd = D[0];
   for (;;) {
-    if (i >= c) {
+    bool more = true;
+    while (i >= c) {
       if (open) {
         if (starts) A.partials[cur] = acc;
         else { A.spill[g] = acc; A.spill_task[g] = cur; }
       }
-      if (j >= P) break;
+      open = false;
+      if (j >= P) { more = false; break; }
       const AffDesc d = nd;
       cur = t0 + j;
       j++;
@@ -326,8 +335,8 @@ B200_HD void aff_thread(const AffArgs<F>& A, uint32_t g, uint32_t T) {
       inb = ceil_shr(s, L) + cur + g;
       acc = XYZZ<F>::inf();
       open = true;
-      continue;
     }
+    if (!more) break;
     if (pfk && i + PF < c) {
       if (L == 0) aff_prefetch(pfk, A.bases + (A.entries[s + i + PF] >> 1));
       else if ((A.tune >> 5) & 1u) aff_prefetch(pfk, &A.lvl[L][inb + i + PF]);

@@ -394,7 +394,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   const bool use_aff = ctx->msm_affine_mode == 2 || (ctx->msm_affine_mode == 1 && m_max >= AFF_AUTO_MIN_ENTRIES);
   if (use_aff) {
     const char* tune_env = getenv("B200G16_AFF_TUNE");   // experiments only (tools/sweep.py --affine)
-    const uint32_t tune = tune_env ? (uint32_t)strtoul(tune_env, nullptr, 0) : 0x11u;
+    const uint32_t tune = tune_env ? (uint32_t)strtoul(tune_env, nullptr, 0) : 0x100u;
     const bool occ4 = sizeof(F) <= 32 && ((tune >> 8) & 1u);
     const unsigned grid = (unsigned)ctx->sm_count * ((sizeof(F) > 32) ? 2u : (occ4 ? 4u : 3u));   // one wave: equal shares per thread
     const uint32_t T = grid * 128u;
