@@ -265,14 +265,13 @@ __global__ void __launch_bounds__(128) k_merkle_paths(const uint8_t* __restrict_
 // ---- the same path recompute for SMALL batches (one WHIR round opens 64..256 paths): one WARP per path.
 // A path is 24 dependent permutations; one thread runs them in ~8 us each, so a round's paths take 0.2 ms however
 // few they are.  Here lane l = x + 5y of a warp holds state lane A[x, y] (lanes 25..31 idle) and a round is four
-// shuffle stages: theta's column parities (4 independent 64-bit shuffles) and D (2), rho + pi as ONE permuting
-// shuffle of the rotated lane, chi (2) — about 130 cycles of latency per round instead of ~650.
+// shuffle stages: theta's column parities (4 independent 64-bit shuffles) and D (2), then rho + pi + chi as ONE stage
+// (three independent shuffles fetch B[x, y], B[x+1, y], B[x+2, y] straight from the rotated pre-pi lanes).
 struct KeccakLaneCtx {
   int l5, l10, l15, l20;   // lanes of the same column (theta parities)
   int xm1, xp1;            // a lane of column x-1 / x+1 (theta's D)
-  int pi_src;              // lane whose rotated value lands here (rho + pi)
   int rot;                 // rho rotation of THIS lane's value before it leaves
-  int c1, c2;              // lanes (x+1, y), (x+2, y) (chi)
+  int s0, s1, s2;          // rho + pi + chi in one stage: the lanes whose rotated values become B[x, y], B[x+1, y], B[x+2, y]
 };
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
@@ -288,11 +287,12 @@ __device__ __forceinline__ KeccakLaneCtx keccak_lane_ctx(int lane) {
   const int l = lane < 25 ? lane : 0, x = l % 5, y = l / 5;
   c.l5 = (l + 5) % 25; c.l10 = (l + 10) % 25; c.l15 = (l + 15) % 25; c.l20 = (l + 20) % 25;
   c.xm1 = (x + 4) % 5 + 5 * y; c.xp1 = (x + 1) % 5 + 5 * y;
-  c.c1 = (x + 1) % 5 + 5 * y; c.c2 = (x + 2) % 5 + 5 * y;
   c.rot = kRot[l];
-  // pi: B[y', 2x' + 3y'] = A[x', y'];  this lane (x, y) receives from the (x', y') with y' = x, 2x' + 3y' = y (mod 5)
-  const int yp = x, xp = ((y - 3 * yp) % 5 + 5) * 3 % 5;   // 2^-1 = 3 (mod 5)
-  c.pi_src = xp + 5 * yp;
+  // pi: B[y', 2x' + 3y'] = A[x', y'];  lane (X, Y) receives from the (x', y') with y' = X, 2x' + 3y' = Y (mod 5);
+  // chi reads B[x+1, y] and B[x+2, y] as well: fetch all three straight from their pre-pi lanes (one shuffle stage
+  // instead of the permuting shuffle followed by chi's two)
+  auto pi_src = [](int X, int Y) { const int yp = X, xp = ((Y - 3 * yp) % 5 + 5) * 3 % 5; return xp + 5 * yp; };   // 2^-1 = 3 (mod 5)
+  c.s0 = pi_src(x, y); c.s1 = pi_src((x + 1) % 5, y); c.s2 = pi_src((x + 2) % 5, y);
   return c;
 }
 
@@ -303,11 +303,9 @@ __device__ __forceinline__ uint64_t keccak_f1600_warp(uint64_t a, const KeccakLa
     const uint64_t col = a ^ shfl64(a, c.l5) ^ shfl64(a, c.l10) ^ shfl64(a, c.l15) ^ shfl64(a, c.l20);
     const uint64_t cm = shfl64(col, c.xm1), cp = shfl64(col, c.xp1);
     a ^= cm ^ ((cp << 1) | (cp >> 63));
-    // rho (rotate own value) + pi (one permuting shuffle)
+    // rho (rotate own value), then pi and chi's operands as three independent shuffles of the rotated lanes
     const uint64_t r = c.rot ? ((a << c.rot) | (a >> (64 - c.rot))) : a;
-    const uint64_t b = shfl64(r, c.pi_src);
-    // chi
-    const uint64_t b1 = shfl64(b, c.c1), b2 = shfl64(b, c.c2);
+    const uint64_t b = shfl64(r, c.s0), b1 = shfl64(r, c.s1), b2 = shfl64(r, c.s2);
     a = b ^ (~b1 & b2);
     if (lane == 0) a ^= kRC[rnd];
   }

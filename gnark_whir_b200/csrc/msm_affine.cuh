@@ -64,18 +64,7 @@ struct AffArgs {
   uint32_t* spill_task;                // task the spill belongs to, AFF_NONE / AFF_EMPTY if none
   int max_levels;
   uint32_t min_pairs;                  // a level is only run if the thread's share yields at least this many pairs
-  uint32_t tune;                       // bits 0-1: prefetch of the NEXT operands (0 none, 1 into L2, 2 into L1); bits 2-4: distance
-                                       // in steps; bit 5: also for levels >= 1 and the parked prefixes
 };
-
-B200_HD void aff_prefetch(uint32_t kind, const void* p) {
-#if defined(__CUDA_ARCH__)
-  if (kind == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  else if (kind == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)kind; (void)p;
-#endif
-}
 
 // NV 128-bit words of a base point: read-only path with a 64-byte L2 fetch granule on the device (a G1 point is one
 // granule and its neighbours in the table are never wanted: the default promotion would double the DRAM traffic)
@@ -179,11 +168,9 @@ B200_HD Affine<F> aff_finish(const Affine<F>& a, const F& bx, const F& num, cons
 
 // One level of the pair tree over the P pieces of thread g (descriptor strip D, first task t0) of share [x0, x1).
 template <class F>
-B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint32_t P, uint32_t x0, uint32_t x1) {
+B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint32_t P) {
   const AffDesc* const D = A.desc + t0 + g;
   Affine<F>* const out = A.lvl[l + 1];
-  const uint32_t pfk = A.tune & 3u, PF = (A.tune >> 2) & 7u;  // prefetch kind / distance in pairs
-  const bool pf_hi = (A.tune >> 5) & 1u;
   // ---- forward: running product of the denominators; the value BEFORE pair q is parked in out[q].x
   F run = F::one();
   {
@@ -213,18 +200,6 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
         open = true;
       }
       if (!more) break;
-      if (pfk) {
-        if (l == 0) {
-          const uint32_t pos = s + 2 * i + 2 * PF;
-          if (pos + 1 < x1) {
-            aff_prefetch(pfk, A.bases + (A.entries[pos] >> 1));
-            aff_prefetch(pfk, A.bases + (A.entries[pos + 1] >> 1));
-          }
-        } else if (pf_hi && i + PF < np) {
-          aff_prefetch(pfk, &A.lvl[l][inb + 2 * (i + PF)]);
-          aff_prefetch(pfk, &A.lvl[l][inb + 2 * (i + PF) + 1]);
-        }
-      }
       const F ax = aff_load_x(A, l, s, inb, 2 * i), bx = aff_load_x(A, l, s, inb, 2 * i + 1);
       F den = F::sub(bx, ax);
       bool live = true;
@@ -261,19 +236,6 @@ B200_HD void aff_level(const AffArgs<F>& A, int l, uint32_t g, uint32_t t0, uint
         outb = ceil_shr(s, l + 1) + tg;
       }
       if (!more) break;
-      if (pfk) {
-        if (l == 0) {
-          const uint32_t pos = s + 2 * (uint32_t)i;
-          if (pos >= x0 + 2 * PF) {
-            aff_prefetch(pfk, A.bases + (A.entries[pos - 2 * PF] >> 1));
-            aff_prefetch(pfk, A.bases + (A.entries[pos - 2 * PF + 1] >> 1));
-          }
-        } else if (pf_hi && i >= (int32_t)PF) {
-          aff_prefetch(pfk, &A.lvl[l][inb + 2 * ((uint32_t)i - PF)]);
-          aff_prefetch(pfk, &A.lvl[l][inb + 2 * ((uint32_t)i - PF) + 1]);
-        }
-        if (pf_hi && i >= (int32_t)PF) aff_prefetch(pfk, &out[outb + (uint32_t)i - PF]);
-      }
       const Affine<F> a = aff_load(A, l, s, inb, 2 * (uint32_t)i), b = aff_load(A, l, s, inb, 2 * (uint32_t)i + 1);
       F den = F::sub(b.x, a.x), num;
       int cls = 0;
@@ -308,9 +270,8 @@ B200_HD void aff_thread(const AffArgs<F>& A, uint32_t g, uint32_t T) {
   const uint32_t M = E / T;
   int L = 0;
   while (L < A.max_levels && (M >> (L + 1)) >= A.min_pairs) L++;
-  for (int l = 0; l < L; l++) aff_level<F>(A, l, g, t0, P, x0, x1);
+  for (int l = 0; l < L; l++) aff_level<F>(A, l, g, t0, P);
   // ---- what is left of every piece: mixed XYZZ chain
-  const uint32_t pfk = A.tune & 3u, PF = (A.tune >> 2) & 7u;
   uint32_t j = 0, i = 0, c = 0, s = 0, inb = 0, cur = 0;
   bool open = false, starts = false;
   XYZZ<F> acc = XYZZ<F>::inf();
@@ -337,10 +298,6 @@ B200_HD void aff_thread(const AffArgs<F>& A, uint32_t g, uint32_t T) {
       open = true;
     }
     if (!more) break;
-    if (pfk && i + PF < c) {
-      if (L == 0) aff_prefetch(pfk, A.bases + (A.entries[s + i + PF] >> 1));
-      else if ((A.tune >> 5) & 1u) aff_prefetch(pfk, &A.lvl[L][inb + i + PF]);
-    }
     acc.madd(aff_load(A, L, s, inb, i));
     i++;
   }
@@ -369,9 +326,12 @@ B200_HD void aff_fixup_thread(XYZZ<F>* partials, const XYZZ<F>* spill, const uin
 }
 
 #if defined(__CUDACC__)
-// G1: ~140 registers -> 3 CTAs of 128 threads per SM (OCC = 4 caps them at 128); G2: 2.
-template <class F, int OCC>
-__global__ void __launch_bounds__(128, OCC) k_accumulate_affine(const AffArgs<F> A) {
+// G1: 128 registers -> 4 CTAs of 128 threads per SM (3 CTAs with the ~140 registers the compiler would like: 10.5 ms
+// against 9.9 at 2^22); G2: 2.  Software prefetch of the next operands into L2 / L1 (prefetch.global) was measured
+// too: slower at every distance (13.1 ms), the address needs the next sorted entry — one more dependent load.
+constexpr int AFF_THREADS = 128;
+template <class F>
+__global__ void __launch_bounds__(AFF_THREADS, (sizeof(F) > 32) ? 2 : 4) k_accumulate_affine(const AffArgs<F> A) {
   aff_thread<F>(A, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 

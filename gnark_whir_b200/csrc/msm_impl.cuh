@@ -393,17 +393,13 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   }
   const bool use_aff = ctx->msm_affine_mode == 2 || (ctx->msm_affine_mode == 1 && m_max >= AFF_AUTO_MIN_ENTRIES);
   if (use_aff) {
-    const char* tune_env = getenv("B200G16_AFF_TUNE");   // experiments only (tools/sweep.py --affine)
-    const uint32_t tune = tune_env ? (uint32_t)strtoul(tune_env, nullptr, 0) : 0x100u;
-    const bool occ4 = sizeof(F) <= 32 && ((tune >> 8) & 1u);
-    const unsigned grid = (unsigned)ctx->sm_count * ((sizeof(F) > 32) ? 2u : (occ4 ? 4u : 3u));   // one wave: equal shares per thread
-    const uint32_t T = grid * 128u;
+    const unsigned grid = (unsigned)ctx->sm_count * ((sizeof(F) > 32) ? 2u : 4u);   // one wave: equal shares per thread
+    const uint32_t T = grid * (uint32_t)AFF_THREADS;
     AffArgs<F> A;
     A.bases = d_bases; A.entries = entries; A.task_bucket = task_bucket; A.offsets = offsets; A.counts = counts;
     A.task_off = task_off; A.totals = totals; A.partials = partials;
     A.max_levels = ctx->msm_affine_levels < 1 ? 1 : (ctx->msm_affine_levels > AFF_LEVELS_MAX ? AFF_LEVELS_MAX : ctx->msm_affine_levels);
     A.min_pairs = ctx->msm_affine_min_pairs;
-    A.tune = tune;
     A.lvl[0] = nullptr;
     for (int l = 1; l <= AFF_LEVELS_MAX; l++) {
       A.lvl[l] = nullptr;
@@ -417,12 +413,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
     B200_TRY(ws.aff_spill_task.ensure((size_t)T * sizeof(uint32_t)));
     A.spill = ws.aff_spill.as<XYZZ<F>>();
     A.spill_task = ws.aff_spill_task.as<uint32_t>();
-    if constexpr (sizeof(F) > 32) {
-      k_accumulate_affine<F, 2><<<grid, 128, 0, st>>>(A);
-    } else {
-      if (occ4) k_accumulate_affine<F, 4><<<grid, 128, 0, st>>>(A);
-      else k_accumulate_affine<F, 3><<<grid, 128, 0, st>>>(A);
-    }
+    k_accumulate_affine<F><<<grid, AFF_THREADS, 0, st>>>(A);
     k_aff_fixup<F><<<cdiv(T, 128), 128, 0, st>>>(partials, A.spill, A.spill_task, T);
     ctx->launches += 1;
   } else {

@@ -60,7 +60,7 @@ static int run_case(uint32_t npts, uint32_t nb, uint32_t mean, int shape, uint32
   }
   std::vector<uint32_t> totals(16, 0);
   totals[0] = E; totals[1] = ntasks; totals[4] = seg;
-  const uint32_t T = grid * 128u;
+  const uint32_t T = grid * (uint32_t)AFF_THREADS;
   AffArgs<Fp> A;
   memset(&A, 0, sizeof(A));
   A.bases = to_dev(points); A.entries = to_dev(entries); A.task_bucket = to_dev(task_bucket); A.offsets = to_dev(offsets);
@@ -76,8 +76,8 @@ static int run_case(uint32_t npts, uint32_t nb, uint32_t mean, int shape, uint32
   CK(cudaMalloc(&A.spill, T * sizeof(XYZZ<Fp>)));
   CK(cudaMalloc(&A.spill_task, T * sizeof(uint32_t)));
   CK(cudaMemset(A.spill_task, 0x5a, T * sizeof(uint32_t)));
-  A.max_levels = levels; A.min_pairs = min_pairs; A.tune = 0x11;
-  k_accumulate_affine<Fp, 3><<<grid, 128>>>(A);
+  A.max_levels = levels; A.min_pairs = min_pairs;
+  k_accumulate_affine<Fp><<<grid, AFF_THREADS>>>(A);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   k_aff_fixup<Fp><<<(T + 127) / 128, 128>>>(A.partials, A.spill, A.spill_task, T);

@@ -54,7 +54,7 @@ int run_case(const Affine<F>* points, uint32_t npts, uint32_t nb, uint32_t mean,
     A.lvl[l] = lvl[l].data();
   }
   A.desc = desc.data(); A.spill = spill.data(); A.spill_task = spill_task.data();
-  A.max_levels = levels; A.min_pairs = min_pairs; A.tune = 0x11;
+  A.max_levels = levels; A.min_pairs = min_pairs;
   // The GPU runs the threads concurrently: no scratch slot (level buffers, descriptors) may be written by two of
   // them.  Sequential emulation would hide that, so diff the scratch after every thread and keep an owner map.
   std::vector<std::vector<int>> owner(AFF_LEVELS_MAX + 2);

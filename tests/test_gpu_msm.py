@@ -326,3 +326,18 @@ def test_msm_g1_batch_affine_heavy_bucket_and_table(affine_ctx, rng):
     bases.precompute(14)
     assert np.array_equal(affine_ctx.msm(bases, bn.fr_to_mont_array(ss)), exp)
     bases.free()
+
+
+def test_batch_affine_kernel_harness(tmp_path):
+    """tests/host_harness/affine_gpu.cu: k_accumulate_affine / k_aff_fixup launched directly on synthetic bucket lists
+    (fewer entries than threads, heavy bucket, mostly empty buckets, repeated points + infinity; 1..4 levels) against a
+    host-side bucket sum — the GPU twin of tests/test_affine_host_cpu.py."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "affine_gpu")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "--expt-relaxed-constexpr",
+                    "-I", os.path.join(root, "gnark_whir_b200", "csrc"), os.path.join(root, "tests", "host_harness", "affine_gpu.cu"),
+                    "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-2000:]

@@ -109,37 +109,6 @@ def affine_sweep(ctx):
             del d_uni, d_mix
 
 
-def affine_tune(ctx):
-    """Prefetch kind / distance / occupancy variants of k_accumulate_affine (B200G16_AFF_TUNE), one size."""
-    import os
-    args = [a for a in sys.argv if a.startswith("--logs=")]
-    logn = int(args[0][7:]) if args else 22
-    lv = [a for a in sys.argv if a.startswith("--levels=")]
-    levels = int(lv[0][9:]) if lv else 2
-    tn = [a for a in sys.argv if a.startswith("--tunes=")]
-    tunes = [int(x, 0) for x in tn[0][8:].split(",")] if tn else [0x00, 0x11, 0x09, 0x06, 0x0a, 0x2a, 0x31]
-    n = 1 << logn
-    ks = rand_fr(n)
-    bases = ctx.fixed_base_mul(g16.g1_point(g16.G1_GEN), ks, group=1, resident=True)
-    bases.precompute(0)
-    d_sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
-    want = cport.g1_gen_mul(cport.fr_dot(ks, d_sc.cpu().numpy().view(np.uint64)))
-    ctx.set_msm_batch_affine(2, levels, 0)
-    for occ in (0, 0x100):
-        for tune in tunes:
-            os.environ["B200G16_AFF_TUNE"] = str(tune | occ)
-            best, ok = None, True
-            for _ in range(3):
-                ok = ok and bool(np.array_equal(ctx.msm(bases, d_sc.data_ptr(), n=n), want))
-                ph = ctx.last_timings()
-                if best is None or ph[2] < best[2]:
-                    best = ph
-            emit(config="msm_batch_affine_tune", log2n=logn, levels=levels, tune=hex(tune | occ), accumulate_ms=round(best[2], 3),
-                 bit_exact_vs_oracle=ok)
-    ctx.set_msm_batch_affine(0, 0, 0)
-    bases.free()
-
-
 def affine_debug(ctx):
     """Batched-affine against XYZZ on the same inputs, small sizes, every level count."""
     for logn in (8, 10, 12, 14, 15, 16, 17):
@@ -164,10 +133,6 @@ def main():
     ctx = lib.Context(0)
     if "--windows" in sys.argv:
         window_sweep(ctx)
-        ctx.close()
-        return
-    if "--affine-tune" in sys.argv:
-        affine_tune(ctx)
         ctx.close()
         return
     if "--affine-debug" in sys.argv:
