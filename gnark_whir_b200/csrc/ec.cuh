@@ -22,11 +22,22 @@ struct alignas(16) Fp2 {
   static B200_HD Fp2 dbl(const Fp2& a) { return {Fp::dbl(a.c0), Fp::dbl(a.c1)}; }
   static B200_HD Fp2 neg(const Fp2& a) { return {Fp::neg(a.c0), Fp::neg(a.c1)}; }
   // device: (a0 b0 - a1 b1) + (a0 b1 + a1 b0) u as two fused two-term products (2 x 200 multiply-adds, no
-  // field additions: the G2 kernels are limited by the ALU work around their products);
+  // field additions: the G2 kernels are limited by the ALU work around their products), both inside ONE out-of-line
+  // routine so that the scheduler interleaves the two independent carry chains — the G2 accumulate kernel runs 2 warps
+  // per scheduler (252 registers) and was waiting on fixed-latency dependencies (ncu: stall_wait 3.8 per issue,
+  // pipe_fmaheavy 85%) with one chain at a time;
   // host: Karatsuba, 3 base-field products
+#if defined(__CUDACC__)
+  static __host__ __device__ __noinline__ Fp2 mul_pair_call(Fp2 a, Fp2 b) {
+    return {Fp::mul_sub(a.c0, b.c0, a.c1, b.c1), Fp::mul_add(a.c0, b.c1, a.c1, b.c0)};
+  }
+  static __host__ __device__ __noinline__ Fp2 sqr_pair_call(Fp2 a) {
+    return {Fp::mul(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1)), Fp::dbl(Fp::mul(a.c0, a.c1))};
+  }
+#endif
   static B200_HD Fp2 mul(const Fp2& a, const Fp2& b) {
 #if defined(__CUDA_ARCH__)
-    return {Fp::mul_sub_call(a.c0, b.c0, a.c1, b.c1), Fp::mul_add_call(a.c0, b.c1, a.c1, b.c0)};
+    return mul_pair_call(a, b);
 #else
     Fp t0 = Fp::mul_call(a.c0, b.c0);
     Fp t1 = Fp::mul_call(a.c1, b.c1);
@@ -37,9 +48,13 @@ struct alignas(16) Fp2 {
   static B200_HD Fp2 mul_sub(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) { return sub(mul(a, b), mul(c, d)); }
   // (a0+a1)(a0-a1) + 2 a0 a1 u : 2 products
   static B200_HD Fp2 sqr(const Fp2& a) {
+#if defined(__CUDA_ARCH__)
+    return sqr_pair_call(a);
+#else
     Fp t0 = Fp::mul_call(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1));
     Fp t1 = Fp::mul_call(a.c0, a.c1);
     return {t0, Fp::dbl(t1)};
+#endif
   }
   static B200_HD Fp2 inv(const Fp2& a) {
     Fp n = Fp::inv(Fp::add(Fp::sqr(a.c0), Fp::sqr(a.c1)));

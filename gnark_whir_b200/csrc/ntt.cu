@@ -11,13 +11,14 @@
 //            multiplies by g^-i/N last (index bit-reversed when DIF); g = 5.
 //
 // Kernel structure: log2 N levels are split into passes of <= 8 levels.  A pass owns the index
-// bits [b0, b0+k): a CTA loads a tile of 2^k "rows" x 8 contiguous "columns" (256 B chunks,
-// coalesced) into shared memory, runs the k radix-2 levels there (split lo/hi uint4 layout so
+// bits [b0, b0+k): a CTA of 64 threads loads a tile of 2^k "rows" x 2 contiguous "columns" (16 KB)
+// into shared memory, runs the k radix-2 levels there (split lo/hi uint4 layout so
 // consecutive lanes hit consecutive banks), and stores the tile back: 64 B of HBM traffic per
-// element per pass.  Coset / 1/N scaling rides on the first pass's load or the last pass's
-// store.  Twiddles come from one table w^e (e < N/2): the pass over the top bits streams it
+// element per pass; ~14 such CTAs share an SM and overlap each other's load / butterfly / store phases.
+// Coset / 1/N scaling rides on the first pass's load or the last pass's
+// store.  Twiddles come from one table w^e (e <= N/2): the pass over the top bits streams it
 // once, later passes reuse a few KB of it out of L1/L2; inverse transforms read the same table
-// through w^-e = -w^(N/2-e).
+// through w^-e = -w^(N/2-e) with the sign folded into the butterfly.
 #include "common.cuh"
 #include "field.cuh"
 
@@ -25,7 +26,8 @@ namespace b200 {
 
 constexpr int NTT_MAX_K = 8;
 constexpr int NTT_LOGC = 3;
-constexpr int NTT_THREADS = 256;
+constexpr int NTT_THREADS = 64;    // 2 warps per CTA, ~14 CTAs per SM (profiles/r02j_ntt_config_sweep.txt)
+constexpr int NTT_CTAS = 14;
 
 static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -98,8 +100,9 @@ struct NttPassArgs {
 // barriers fewer per pass — is 1.4% SLOWER at 2^24 (3.906 vs 3.853 ms): the separate load loop keeps four independent
 // 32-byte loads per thread in flight, the fused form exposes the latency of two.)
 // TFAST: rows contiguous in memory (b0 == 0) -> row index fastest in shared memory.
-template <bool DIT, bool TFAST>
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
+// INV: inverse transform (twiddles w^-e), a template parameter so that the forward kernels carry none of its selects.
+template <bool DIT, bool TFAST, bool INV>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_CTAS) k_ntt_pass(NttPassArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = A.k, L = A.L, b0 = A.b0, logc = A.logc;
   const uint32_t rows = 1u << k;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
   const Fr* post = (A.post_mode == 2 && A.nvecs) ? A.post_vec[blockIdx.y] : A.post;
 
   // ---- load
-  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+  for (uint32_t x = threadIdx.x; x < T; x += blockDim.x) {
     uint32_t t, c;
     if (TFAST) { t = x & (rows - 1); c = x >> k; }
     else { c = x & ((1u << logc) - 1); t = x >> logc; }
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
     const int lb = DIT ? step : (k - 1 - step);  // local partner bit
     const int pb = b0 + lb;                      // global partner bit
     const uint32_t lbmask = (1u << lb) - 1u;
-    for (uint32_t q = threadIdx.x; q < nbf; q += NTT_THREADS) {
+    for (uint32_t q = threadIdx.x; q < nbf; q += blockDim.x) {
       uint32_t r, c;
       if (TFAST) { r = q & ((rows >> 1) - 1); c = q >> (k - 1); }
       else { c = q & ((1u << logc) - 1); r = q >> logc; }
@@ -146,21 +149,30 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(NttPassArgs A) {
       uint32_t u = (tile << logc) + c;
       uint32_t j = ((t0 & lbmask) << b0) | (u & lowmask);
       uint32_t e = j << (L - 1 - pb);
-      Fr w = twiddle(A.tw, e, A.tw_sh, A.tw_half, A.inverse);
+      // Inverse transforms need w^-e = -w^(N/2 - e).  The table carries one entry more than N/2 (w^(N/2) = -1), so
+      // the lookup is branch-free for every e, and the sign goes into the butterfly instead of a field negation per
+      // twiddle: (x - y) * (-w') = (y - x) * w', and x +- y * (-w') = x -+ y * w'.
+      const uint32_t idx = e << A.tw_sh;
+      const Fr w = ldg_fr(A.tw + (INV ? A.tw_half - idx : idx));
       if (DIT) {
         yv = Fr::mul(yv, w);
-        sm.put(s0, Fr::add(xv, yv));
-        sm.put(s1, Fr::sub(xv, yv));
+        if (!INV) {
+          sm.put(s0, Fr::add(xv, yv));
+          sm.put(s1, Fr::sub(xv, yv));
+        } else {
+          sm.put(s0, Fr::sub(xv, yv));
+          sm.put(s1, Fr::add(xv, yv));
+        }
       } else {
         sm.put(s0, Fr::add(xv, yv));
-        sm.put(s1, Fr::mul(Fr::sub(xv, yv), w));
+        sm.put(s1, Fr::mul(INV ? Fr::sub(yv, xv) : Fr::sub(xv, yv), w));
       }
     }
     __syncthreads();
   }
 
   // ---- store
-  for (uint32_t x = threadIdx.x; x < T; x += NTT_THREADS) {
+  for (uint32_t x = threadIdx.x; x < T; x += blockDim.x) {
     uint32_t t, c;
     if (TFAST) { t = x & (rows - 1); c = x >> k; }
     else { c = x & ((1u << logc) - 1); t = x >> logc; }
@@ -349,15 +361,15 @@ static void domain_params(int L, NttDomain* d) {
   d->n_inv = Fr::inv(fr_from_u64(1ull << L));
 }
 
-// twiddle table w^e, e < N/2, for the largest N seen so far
+// twiddle table w^e, e <= N/2, for the largest N seen so far
 static int ensure_twiddles(b200g16_ctx* ctx, int L) {
   NttWorkspace& ws = ctx->ntt;
   if (ws.tw_log >= L) return 0;
   size_t half = (size_t)1 << (L > 0 ? L - 1 : 0);
-  B200_TRY(ws.tw.ensure(half * sizeof(Fr)));
+  B200_TRY(ws.tw.ensure((half + 1) * sizeof(Fr)));   // + w^(N/2) = -1: k_ntt_pass reads w^(N/2 - e) for inverse transforms
   NttDomain d;
   domain_params(L, &d);
-  B200_TRY(build_geometric(ctx, ws.tw.as<Fr>(), half, Fr::one(), d.w));
+  B200_TRY(build_geometric(ctx, ws.tw.as<Fr>(), half + 1, Fr::one(), d.w));
   ws.tw_log = L;
   return 0;
 }
@@ -443,25 +455,28 @@ static int ntt_device_impl(b200g16_ctx* ctx, Fr* d_data, Fr* const* vecs, int L,
     A.post_mode = (p == npass - 1) ? post_mode : 0;
     A.post = post;
     A.post_bitrev = post_bitrev;
-    // tile = 2^k rows x 2^logc columns (8 columns = 256 B chunks unless the vector is tiny)
-    // 8-level passes of large transforms: 4 columns (32 KB tiles, 4 CTAs/SM) overlap the load / store phases
-    // of one CTA with the butterflies of the others better than 8 columns (64 KB, 3 CTAs/SM); measured:
-    // 2^24 3.98 -> 3.85 ms.  Shorter passes (2^20: 7+7+6, 2^26: 7+7+6+6 levels) keep 8 columns.
-    const int logc_pref = (A.k == NTT_MAX_K && L >= 22) ? NTT_LOGC - 1 : NTT_LOGC;
+    // tile = 2^k rows x 2^logc columns.  Measured (profiles/r02j_ntt_config_sweep.txt, 2^20 .. 2^24): what matters is
+    // ~8 elements per thread per tile in SMALL CTAs — 64 threads x 2 columns (16 KB tiles, 14 CTAs/SM): barriers span 2
+    // warps instead of 8 and many CTAs interleave their load / butterfly / store phases.  2^24: 3.78 -> 3.54 ms against
+    // 256 threads x 4 columns, computeH 27.6 -> 25.9 ms; 8 columns x 256 threads (round 1): 3.86 ms.
+    const int logc_pref = 1;
     int logc = L - A.k < logc_pref ? L - A.k : logc_pref;
     A.logc = logc;
     size_t tiles = n >> (A.k + logc);
     size_t smem = ((size_t)1 << (A.k + logc)) * sizeof(Fr);
     dim3 grid((unsigned)tiles, (unsigned)batch);
     bool tfast = (A.b0 == 0);
-#define B200_LAUNCH_PASS(DITV, TF)                                                                          \
+    const unsigned ntt_threads = NTT_THREADS;
+#define B200_LAUNCH_PASS(DITV, TF, IV)                                                                      \
     do {                                                                                                     \
-      B200_CUDA(cudaFuncSetAttribute(k_ntt_pass<DITV, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      B200_CUDA(cudaFuncSetAttribute(k_ntt_pass<DITV, TF, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)(((size_t)1 << (NTT_MAX_K + NTT_LOGC)) * sizeof(Fr))));            \
-      k_ntt_pass<DITV, TF><<<grid, NTT_THREADS, smem, ctx->stream>>>(A);                                     \
+      k_ntt_pass<DITV, TF, IV><<<grid, ntt_threads, smem, ctx->stream>>>(A);                                 \
     } while (0)
-    if (dit) { if (tfast) B200_LAUNCH_PASS(true, true); else B200_LAUNCH_PASS(true, false); }
-    else { if (tfast) B200_LAUNCH_PASS(false, true); else B200_LAUNCH_PASS(false, false); }
+#define B200_LAUNCH_PASS2(DITV, TF) do { if (A.inverse) B200_LAUNCH_PASS(DITV, TF, true); else B200_LAUNCH_PASS(DITV, TF, false); } while (0)
+    if (dit) { if (tfast) B200_LAUNCH_PASS2(true, true); else B200_LAUNCH_PASS2(true, false); }
+    else { if (tfast) B200_LAUNCH_PASS2(false, true); else B200_LAUNCH_PASS2(false, false); }
+#undef B200_LAUNCH_PASS2
 #undef B200_LAUNCH_PASS
     ctx->launches++;
   }
