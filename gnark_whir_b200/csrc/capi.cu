@@ -62,7 +62,7 @@ static int fixed_base_entry(b200g16_ctx* ctx, const uint64_t* base, const uint64
   return st;
 }
 
-// Host scalars of a large MSM are uploaded in MSM_PIPE_CHUNKS pieces on a copy stream; piece j's
+// Host scalars of a large MSM are uploaded in MSM_PIPE_CHUNKS pieces of growing size on a copy stream; piece j's
 // sub-MSM (its own point sub-range, its own result slot) runs while piece j+1 is still crossing PCIe,
 // and the host adds the partial results.  Below MSM_PIPE_MIN points one copy + one MSM is faster.
 constexpr size_t MSM_PIPE_MIN = (size_t)1 << 20;
@@ -90,7 +90,18 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     MsmCfg cfg[MSM_PIPE_CHUNKS];
     size_t lo[MSM_PIPE_CHUNKS + 1];
     const int pieces = n >= ((size_t)1 << 22) ? MSM_PIPE_CHUNKS : 2;
-    for (int j = 0; j <= pieces; j++) lo[j] = n * (size_t)j / pieces;
+    // Pinned (or registered) host memory: geometric pieces (1 : 2 : 4 : 8) — only the FIRST piece's copy is exposed,
+    // so it is the smallest, and each later piece's copy hides behind the sub-MSM of the piece before it (a sub-MSM
+    // takes 2-4x as long as its own copy): 2^24 end to end 41.1 -> 39.6 ms, 2^22 12.2 -> 11.9 ms (3, 5 or 6 pieces: no
+    // better).  Pageable memory is staged by the driver at a fifth of that rate and the pipeline is copy-bound: there
+    // equal pieces win (the LAST sub-MSM is what is exposed; measured 57.8 ms against 68 with geometric pieces).
+    cudaPointerAttributes pattr;
+    const bool pinned_src = cudaPointerGetAttributes(&pattr, scalars) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // (an unregistered pointer is not an error worth keeping)
+    const bool geometric = pinned_src && n >= ((size_t)1 << 21);   // (2^20: two equal pieces are 2% faster)
+    for (int j = 0; j <= pieces; j++)
+      lo[j] = geometric ? (size_t)(((unsigned __int128)n * (((size_t)1 << j) - 1)) / (((size_t)1 << pieces) - 1))
+                        : n * (size_t)j / pieces;
     ctx->timings.n = 0;
     for (int j = 0; j < pieces; j++) {
       const size_t m = lo[j + 1] - lo[j];

@@ -144,7 +144,7 @@ struct b200g16_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t tail_stream = nullptr;   // bucket reductions (latency-bound, few threads) overlap the next MSM
   cudaStream_t copy_stream = nullptr;   // H2D of host scalars, pipelined against the MSM of the previous piece
-  cudaEvent_t ev_copy[4] = {};
+  cudaEvent_t ev_copy[8] = {};
   cudaEvent_t ev_front[b200::MSM_SETS] = {}, ev_tail[b200::MSM_SETS] = {};
   bool tail_pending[b200::MSM_SETS] = {};
   int msm_parity = 0;               // next rotating buffer set (0 .. MSM_SETS-1)
