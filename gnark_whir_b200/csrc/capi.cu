@@ -1,6 +1,7 @@
 // extern "C" surface of libb200g16 (see include/b200g16.h for the contract and the
 // gnark / gnark-crypto routines each entry point replaces).
 #include "msm_impl.cuh"
+#include "host_copy.cuh"
 
 namespace b200 {
 // instantiated in msm_g1.cu / msm_g2.cu
@@ -90,22 +91,19 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     MsmCfg cfg[MSM_PIPE_CHUNKS];
     size_t lo[MSM_PIPE_CHUNKS + 1];
     const int pieces = n >= ((size_t)1 << 22) ? MSM_PIPE_CHUNKS : 2;
-    // Pinned (or registered) host memory: geometric pieces (1 : 2 : 4 : 8) — only the FIRST piece's copy is exposed,
-    // so it is the smallest, and each later piece's copy hides behind the sub-MSM of the piece before it (a sub-MSM
-    // takes 2-4x as long as its own copy): 2^24 end to end 41.1 -> 39.6 ms, 2^22 12.2 -> 11.9 ms (3, 5 or 6 pieces: no
-    // better).  Pageable memory is staged by the driver at a fifth of that rate and the pipeline is copy-bound: there
-    // equal pieces win (the LAST sub-MSM is what is exposed; measured 57.8 ms against 68 with geometric pieces).
-    cudaPointerAttributes pattr;
-    const bool pinned_src = cudaPointerGetAttributes(&pattr, scalars) == cudaSuccess && pattr.type == cudaMemoryTypeHost;
-    cudaGetLastError();   // (an unregistered pointer is not an error worth keeping)
-    const bool geometric = pinned_src && n >= ((size_t)1 << 21);   // (2^20: two equal pieces are 2% faster)
+    // Geometric pieces (1 : 2 : 4 : 8): only the FIRST piece's copy is exposed, so it is the smallest, and each later
+    // piece's copy hides behind the sub-MSM of the piece before it (a sub-MSM takes 2-4x as long as its own copy).
+    // 2^24 end to end from pinned memory 41.1 -> 39.6 ms, 2^22 12.2 -> 11.9 ms (3, 5 or 6 pieces: no better); from
+    // pageable memory, staged by h2d_copy's host threads, 43.2 -> 41.0 ms.  (With the DRIVER staging pageable memory
+    // at ~10 GB/s the pipeline was copy-bound and equal pieces won: 57.8 ms.)
+    const bool geometric = n >= ((size_t)1 << 21);   // (2^20: two equal pieces are 2% faster)
     for (int j = 0; j <= pieces; j++)
       lo[j] = geometric ? (size_t)(((unsigned __int128)n * (((size_t)1 << j) - 1)) / (((size_t)1 << pieces) - 1))
                         : n * (size_t)j / pieces;
     ctx->timings.n = 0;
     for (int j = 0; j < pieces; j++) {
       const size_t m = lo[j + 1] - lo[j];
-      B200_CUDA(cudaMemcpyAsync(d + lo[j], h + lo[j], m * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      B200_TRY(h2d_copy(ctx, d + lo[j], h + lo[j], m * sizeof(Fr), ctx->copy_stream));
       B200_CUDA(cudaEventRecord(ctx->ev_copy[j], ctx->copy_stream));
       B200_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[j], 0));
       const Affine<F>* pts = msm_operand<F>(bases, offset + lo[j], &tab, &tp);
@@ -124,7 +122,7 @@ static int msm_entry(b200g16_ctx* ctx, const b200g16_bases* bases, int group, si
     const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
     if (!scalars_on_device && n) {
       B200_TRY(ctx->msm.scalars.ensure(n * sizeof(Fr)));
-      B200_CUDA(cudaMemcpyAsync(ctx->msm.scalars.p, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+      B200_TRY(h2d_copy(ctx, ctx->msm.scalars.p, scalars, n * sizeof(Fr), ctx->stream));
       d_scalars = ctx->msm.scalars.as<Fr>();
     }
     const Affine<F>* pts = msm_operand<F>(bases, offset, &tab, &tp);
@@ -270,6 +268,7 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < MSM_SETS; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
   for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
+  h2d_stager_release(ctx);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->tail_stream);
   cudaStreamDestroy(ctx->stream);
@@ -417,7 +416,7 @@ int b200g16_ntt(b200g16_ctx* ctx, uint64_t* data, unsigned log2n, int inverse, i
   B200_CUDA(cudaSetDevice(ctx->device));
   size_t bytes = ((size_t)1 << log2n) * sizeof(Fr);
   B200_TRY(ctx->ntt.a.ensure(bytes));
-  B200_CUDA(cudaMemcpyAsync(ctx->ntt.a.p, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(h2d_copy(ctx, ctx->ntt.a.p, data, bytes, ctx->stream));
   B200_TRY(ntt_device(ctx, ctx->ntt.a.as<Fr>(), (int)log2n, 1, inverse != 0, coset != 0, decimation));
   B200_CUDA(cudaMemcpyAsync(data, ctx->ntt.a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -456,7 +455,7 @@ int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, co
   const uint64_t* src[3] = {a, b, c};
   for (int i = 0; i < 3; i++) {
     B200_TRY(bufs[i]->ensure(n * sizeof(Fr)));
-    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    B200_TRY(h2d_copy(ctx, bufs[i]->p, src[i], n_constraints * sizeof(Fr), ctx->stream));
     if (n > n_constraints)  // computeH pads a, b, c with zeros up to the domain cardinality
       B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (n - n_constraints) * sizeof(Fr),
                                 ctx->stream));

@@ -130,6 +130,15 @@ struct DistH {
   bool ready = false;        // every peer pointer set
 };
 
+// pinned bounce buffers + per-worker streams of h2d_copy (host_copy.cuh): large pageable host buffers -> device
+constexpr int H2D_MAX_WORKERS = 8;
+struct H2DStager {
+  void* pinned = nullptr;            // workers x 2 slots
+  int workers = 0;
+  cudaStream_t stream[H2D_MAX_WORKERS] = {};
+  cudaEvent_t done[H2D_MAX_WORKERS] = {}, slot_free[H2D_MAX_WORKERS][2] = {}, start = nullptr;
+};
+
 struct Timings {
   // last-call device timings in ms (CUDA events on ctx stream); index = phase
   float ms[16];
@@ -160,6 +169,7 @@ struct b200g16_ctx {
   b200::NttWorkspace ntt;
   b200::DistH dist_h;
   b200::DevBuf io_a, io_b, io_c;  // staging for host-pointer entry points
+  b200::H2DStager stager;
   b200::Timings timings = {};
   int msm_window_override = 0;  // 0 = auto
   int msm_affine_mode = 0;      // batched-affine accumulation: 0 = never, 1 = by size, 2 = always

@@ -16,6 +16,7 @@
 //   Bs1 = B1 + beta + s*delta           Bs = B2 + beta2 + s*delta2
 //   Krs = K + Z + (-rs)*delta + s*Ar + r*Bs1
 #include "prove.cuh"
+#include "host_copy.cuh"
 
 namespace b200 {
 
@@ -287,26 +288,39 @@ int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires,
   int ev = 0;
   cudaEventRecord(ctx->ev[ev++], st);
   B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
-  B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  // a, b, c cross PCIe on the copy stream while the witness MSMs already run (prove_device waits on ev_copy[0])
+  B200_TRY(h2d_copy(ctx, ctx->io_a.p, wires, n_wires * sizeof(Fr), st));
+  // The witness goes first: it gates the four MSMs, which are enqueued BEFORE a, b, c are touched — a copy from
+  // pageable memory (a Go slice) occupies the calling thread while it is staged, and the GPU should already be busy.
+  // a, b, c then cross PCIe on the copy stream under those MSMs.
   DevBuf* bufs[3] = {&ctx->ntt.a, &ctx->ntt.b, &ctx->ntt.c};
   const uint64_t* src[3] = {a, b, c};
   cudaStream_t cs = ctx->copy_stream;
-  B200_CUDA(cudaEventRecord(ctx->ev_copy[1], st));       // the witness goes first: it gates the MSMs
-  B200_CUDA(cudaStreamWaitEvent(cs, ctx->ev_copy[1], 0));
-  for (int i = 0; i < 3; i++) {
-    B200_TRY(bufs[i]->ensure(N * sizeof(Fr)));
-    B200_CUDA(cudaMemcpyAsync(bufs[i]->p, src[i], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, cs));
-    if (N > n_constraints)
-      B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), cs));
-  }
-  B200_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
+  for (int i = 0; i < 3; i++) B200_TRY(bufs[i]->ensure(N * sizeof(Fr)));   // (no allocation once the MSMs are in flight)
+  B200_CUDA(cudaEventRecord(ctx->ev_copy[1], st));
   cudaEventRecord(ctx->ev[ev++], st);
   Fr fr_r, fr_s;
   memcpy(&fr_r, r, 32);
   memcpy(&fr_s, s, 32);
-  B200_TRY(prove_device(ctx, pk, ctx->io_a.as<Fr>(), ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(),
-                        fr_r, fr_s, proof_out, &ev, ctx->ev_copy[0]));
+  B200_TRY(prove_front(ctx, pk, ctx->io_a.as<Fr>(), &ev));
+  auto middle = [&]() -> int {
+    B200_CUDA(cudaStreamWaitEvent(cs, ctx->ev_copy[1], 0));   // the buffers' previous readers (an earlier prove) are done
+    for (int i = 0; i < 3; i++) {
+      B200_TRY(h2d_copy(ctx, bufs[i]->p, src[i], n_constraints * sizeof(Fr), cs));
+      if (N > n_constraints)
+        B200_CUDA(cudaMemsetAsync((char*)bufs[i]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), cs));
+    }
+    B200_CUDA(cudaEventRecord(ctx->ev_copy[0], cs));
+    B200_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy[0], 0));
+    return compute_h_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), (int)pk->log2n, false);
+  };
+  if (int status = middle()) {       // leave the ctx usable: the four MSMs in flight are drained and forgotten
+    msm_join(ctx);
+    cudaStreamSynchronize(st);
+    ctx->prove_active = false;
+    return status;
+  }
+  if (ev < 18) cudaEventRecord(ctx->ev[ev++], st);
+  B200_TRY(prove_back(ctx, pk, ctx->ntt.a.as<Fr>(), fr_r, fr_s, proof_out, &ev));
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
   if (h_out) B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));
