@@ -16,6 +16,7 @@
 #include <thread>
 
 #include "prove.cuh"
+#include "host_copy.cuh"
 
 using namespace b200;
 
@@ -339,13 +340,13 @@ static int group_prove_dist(b200g16_group* g, const b200g16_group_pk* gpk, const
       cudaEventRecord(ctx->ev[ev++], stm);
       // witness on the copy stream, this device's slices of a, b, c (zero padded) on the main stream
       B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
-      B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      B200_TRY(h2d_copy(ctx, ctx->io_a.p, wires, n_wires * sizeof(Fr), ctx->copy_stream));
       B200_CUDA(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
       const size_t lo = (size_t)i * M;
       const size_t have = n_constraints > lo ? (n_constraints - lo < M ? n_constraints - lo : M) : 0;
       for (int v = 0; v < 3; v++) {
         char* dst = (char*)D.slice[v].p;
-        if (have) B200_CUDA(cudaMemcpyAsync(dst, src[v] + lo * 4, have * sizeof(Fr), cudaMemcpyHostToDevice, stm));
+        if (have) B200_TRY(h2d_copy(ctx, dst, src[v] + lo * 4, have * sizeof(Fr), stm));
         if (have < M) B200_CUDA(cudaMemsetAsync(dst + have * sizeof(Fr), 0, (M - have) * sizeof(Fr), stm));
       }
       B200_CUDA(cudaEventRecord(g->ev_stage[0][i], stm));
@@ -425,13 +426,13 @@ int b200g16_group_prove(b200g16_group* g, const b200g16_group_pk* gpk, const uin
       cudaEventRecord(ctx->ev[ev++], stm);
       // the witness crosses PCIe on the copy stream while this device's share of computeH runs
       B200_TRY(ctx->io_a.ensure((n_wires ? n_wires : 1) * sizeof(Fr)));
-      B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, wires, n_wires * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy_stream));
+      B200_TRY(h2d_copy(ctx, ctx->io_a.p, wires, n_wires * sizeof(Fr), ctx->copy_stream));
       B200_CUDA(cudaEventRecord(ctx->ev_copy[1], ctx->copy_stream));
       DevBuf* bufs[3] = {&ctx->ntt.a, &ctx->ntt.b, &ctx->ntt.c};
       for (int v = 0; v < 3; v++) {
         if (vector_owner(v, n) != i) continue;
         B200_TRY(bufs[v]->ensure(N * sizeof(Fr)));
-        B200_CUDA(cudaMemcpyAsync(bufs[v]->p, src[v], n_constraints * sizeof(Fr), cudaMemcpyHostToDevice, stm));
+        B200_TRY(h2d_copy(ctx, bufs[v]->p, src[v], n_constraints * sizeof(Fr), stm));
         if (N > n_constraints)
           B200_CUDA(cudaMemsetAsync((char*)bufs[v]->p + n_constraints * sizeof(Fr), 0, (N - n_constraints) * sizeof(Fr), stm));
         Fr* one[1] = {bufs[v]->as<Fr>()};

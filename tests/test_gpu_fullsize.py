@@ -113,3 +113,24 @@ def test_keccak_merkle_2p20_paths(ctx):
         np.stack([np.frombuffer(b"".join(o[1]), np.uint8).reshape(h2 - 1, 32) for o in opened]),
         np.arange(1 << h2, dtype=np.uint64), expected_root=lv[-1][0])
     assert okf.all()
+
+
+def test_pageable_host_buffers_take_the_staged_copy_and_match(ctx):
+    """Large buffers in ordinary (pageable) host memory — what a Go slice is — are staged by the library's own host
+    threads (csrc/host_copy.cuh).  An odd-sized MSM (the last chunk is partial, the upload pieces are uneven) and an
+    NTT through the host-pointer entry points must equal the same calls on device-resident inputs."""
+    rs = np.random.Generator(np.random.PCG64(77))
+    n = (1 << 21) + 4321                                   # 64 MiB + a bit of scalars: two geometric pieces, 8 stripes
+    ks, sc = _rand_fr(rs, n), _rand_fr(rs, n)
+    bases = ctx.fixed_base_mul(bn.g1_to_array([bn.G1_GEN])[0], ks, group=1, resident=True)
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    want = ctx.msm(bases, d_sc.data_ptr(), n=n)
+    assert np.array_equal(ctx.msm(bases, sc), want)         # numpy array = pageable
+    assert np.array_equal(want, cport.g1_gen_mul(cport.fr_dot(ks, sc)))
+    bases.free()
+    logn = 21
+    a = _rand_fr(rs, 1 << logn)
+    d_a = torch.from_numpy(a.view(np.int64)).cuda()
+    ctx.ntt_dev(d_a.data_ptr(), logn, decimation=lib.DIF)
+    got = ctx.ntt(a, decimation=lib.DIF)                    # host-pointer entry point: 64 MiB up, 64 MiB back
+    assert np.array_equal(got, d_a.cpu().numpy().view(np.uint64))
