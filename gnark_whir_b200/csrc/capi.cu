@@ -418,8 +418,7 @@ int b200g16_ntt(b200g16_ctx* ctx, uint64_t* data, unsigned log2n, int inverse, i
   B200_TRY(ctx->ntt.a.ensure(bytes));
   B200_TRY(h2d_copy(ctx, ctx->ntt.a.p, data, bytes, ctx->stream));
   B200_TRY(ntt_device(ctx, ctx->ntt.a.as<Fr>(), (int)log2n, 1, inverse != 0, coset != 0, decimation));
-  B200_CUDA(cudaMemcpyAsync(data, ctx->ntt.a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  B200_TRY(d2h_copy(ctx, data, ctx->ntt.a.p, bytes, ctx->stream));
   return 0;
 }
 
@@ -461,7 +460,7 @@ int b200g16_compute_h(b200g16_ctx* ctx, const uint64_t* a, const uint64_t* b, co
                                 ctx->stream));
   }
   B200_TRY(compute_h_device(ctx, ctx->ntt.a.as<Fr>(), ctx->ntt.b.as<Fr>(), ctx->ntt.c.as<Fr>(), (int)log2n, true));
-  B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, n * sizeof(Fr), cudaMemcpyDeviceToHost));
+  B200_TRY(d2h_copy(ctx, h_out, ctx->ntt.a.p, n * sizeof(Fr), ctx->stream));
   return 0;
 }
 
@@ -481,10 +480,9 @@ int b200g16_keccak_f_batch(b200g16_ctx* ctx, uint64_t* states, size_t n) {
   B200_CUDA(cudaSetDevice(ctx->device));
   size_t bytes = n * 200;
   B200_TRY(ctx->io_a.ensure(bytes));
-  B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  B200_TRY(h2d_copy(ctx, ctx->io_a.p, states, bytes, ctx->stream));
   B200_TRY(keccak_f_batch_device(ctx, ctx->io_a.as<uint64_t>(), n));
-  B200_CUDA(cudaMemcpyAsync(states, ctx->io_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  B200_TRY(d2h_copy(ctx, states, ctx->io_a.p, bytes, ctx->stream));
   return 0;
 }
 
@@ -496,10 +494,9 @@ int b200g16_keccak_sponge_batch(b200g16_ctx* ctx, const uint8_t* inputs, size_t 
   B200_CUDA(cudaSetDevice(ctx->device));
   B200_TRY(ctx->io_a.ensure(n * in_len + 8));
   B200_TRY(ctx->io_b.ensure(n * out_len));
-  if (in_len) B200_CUDA(cudaMemcpyAsync(ctx->io_a.p, inputs, n * in_len, cudaMemcpyHostToDevice, ctx->stream));
+  if (in_len) B200_TRY(h2d_copy(ctx, ctx->io_a.p, inputs, n * in_len, ctx->stream));
   B200_TRY(sponge_batch_device(ctx, ctx->io_a.as<uint8_t>(), in_len, n, ctx->io_b.as<uint8_t>(), out_len));
-  B200_CUDA(cudaMemcpyAsync(outputs, ctx->io_b.p, n * out_len, cudaMemcpyDeviceToHost, ctx->stream));
-  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  B200_TRY(d2h_copy(ctx, outputs, ctx->io_b.p, n * out_len, ctx->stream));
   return 0;
 }
 
@@ -537,9 +534,9 @@ int b200g16_keccak_merkle_paths(b200g16_ctx* ctx, const uint8_t* leaves, size_t 
   B200_TRY(ctx->io_a.ensure(total));
   char* d = ctx->io_a.as<char>();
   cudaStream_t st = ctx->stream;
-  B200_CUDA(cudaMemcpyAsync(d, leaves, sz_leaves, cudaMemcpyHostToDevice, st));
+  B200_TRY(h2d_copy(ctx, d, leaves, sz_leaves, st));
   B200_CUDA(cudaMemcpyAsync(d + o_sib, siblings, sz_sib, cudaMemcpyHostToDevice, st));
-  if (sz_auth) B200_CUDA(cudaMemcpyAsync(d + o_auth, auth_paths, sz_auth, cudaMemcpyHostToDevice, st));
+  if (sz_auth) B200_TRY(h2d_copy(ctx, d + o_auth, auth_paths, sz_auth, st));
   B200_CUDA(cudaMemcpyAsync(d + o_idx, indexes, sz_idx, cudaMemcpyHostToDevice, st));
   if (expected_root) B200_CUDA(cudaMemcpyAsync(d + o_root, expected_root, 32, cudaMemcpyHostToDevice, st));
   B200_TRY(merkle_paths_device(ctx, (const uint8_t*)d, leaf_len, (const uint64_t*)(d + o_sib),

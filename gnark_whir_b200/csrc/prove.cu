@@ -323,7 +323,7 @@ int b200g16_prove(b200g16_ctx* ctx, const b200g16_pk* pk, const uint64_t* wires,
   B200_TRY(prove_back(ctx, pk, ctx->ntt.a.as<Fr>(), fr_r, fr_s, proof_out, &ev));
   ctx->timings.n = ev - 1;
   for (int i = 0; i + 1 < ev; i++) cudaEventElapsedTime(&ctx->timings.ms[i], ctx->ev[i], ctx->ev[i + 1]);
-  if (h_out) B200_CUDA(cudaMemcpy(h_out, ctx->ntt.a.p, N * sizeof(Fr), cudaMemcpyDeviceToHost));
+  if (h_out) B200_TRY(d2h_copy(ctx, h_out, ctx->ntt.a.p, N * sizeof(Fr), ctx->stream));
   return 0;
 }
 

@@ -134,3 +134,9 @@ def test_pageable_host_buffers_take_the_staged_copy_and_match(ctx):
     ctx.ntt_dev(d_a.data_ptr(), logn, decimation=lib.DIF)
     got = ctx.ntt(a, decimation=lib.DIF)                    # host-pointer entry point: 64 MiB up, 64 MiB back
     assert np.array_equal(got, d_a.cpu().numpy().view(np.uint64))
+    # Keccak-f batch through host memory: 40 MB of states up and back, an odd count (partial last chunk)
+    nst = 200_003
+    st = rs.integers(0, 1 << 63, size=(nst, 25), dtype=np.uint64)
+    d_st = torch.from_numpy(st.view(np.int64)).cuda()
+    ctx.keccak_f_batch_dev(d_st.data_ptr(), nst)
+    assert np.array_equal(ctx.keccak_f_batch(st), d_st.cpu().numpy().view(np.uint64))
