@@ -136,8 +136,12 @@ struct alignas(16) XYZZ {
     zzz = F::mul(zzz, PPP);
   }
 
-  // this += q  (add-2008-s)
-  B200_HD_NOINLINE void add(const XYZZ& q) {
+  // this += q  (add-2008-s).  `add` is one out-of-line routine (operands reached through pointers: fine for the
+  // serial tails); `add_inline` is the same code expanded in place for kernels whose whole body is one addition per
+  // thread with both operands in registers (the bucket-reduction tree, msm_impl.cuh).
+  B200_HD_NOINLINE void add(const XYZZ& q) { add_inline(q); }
+
+  B200_HD void add_inline(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
     F U1 = F::mul(x, q.zz);

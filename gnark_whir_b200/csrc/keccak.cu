@@ -16,6 +16,8 @@
 // One thread owns one state: 25 lanes = 50 registers, 24 fully unrolled rounds; chi is a
 // single LOP3 per 32-bit half and theta's 5-way XOR two LOP3s, so the kernel is LOP3/SHF
 // (ALU-pipe) bound, not HBM bound (400 B of traffic per ~3.7k 64-bit logic ops).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -264,13 +266,21 @@ __global__ void __launch_bounds__(128) k_merkle_paths(const uint8_t* __restrict_
 
 // ---- the same path recompute for SMALL batches (one WHIR round opens 64..256 paths): one WARP per path.
 // A path is 24 dependent permutations; one thread runs them in ~8 us each, so a round's paths take 0.2 ms however
-// few they are.  Here lane l = x + 5y of a warp holds state lane A[x, y] (lanes 25..31 idle) and a round is four
-// shuffle stages: theta's column parities (4 independent 64-bit shuffles) and D (2), then rho + pi + chi as ONE stage
-// (three independent shuffles fetch B[x, y], B[x+1, y], B[x+2, y] straight from the rotated pre-pi lanes).
+// few they are.  Here lane l = x + 5y of a warp holds state lane A[x, y] (lanes 25..31 idle) and a round is a few
+// exchange stages between the lanes.  Two exchange mechanisms (template parameter SMEM):
+//   shuffles:       theta's column parities (4 independent 64-bit shuffles) and D (2), then rho + pi + chi as ONE stage
+//                   (three independent shuffles fetch B[x, y], B[x+1, y], B[x+2, y] straight from the rotated pre-pi
+//                   lanes): 18 SHFL in three dependent stages per round;
+//   shared memory:  the warp parks the state in a 25-lane shared array; every lane reads the two neighbouring COLUMNS
+//                   (10 independent LDS.64) and forms theta's D by itself, parks the rotated value in a second array
+//                   and reads chi's three operands from their pre-pi slots: two store -> load round trips per round,
+//                   one 64-bit access where the shuffle path needs two 32-bit ones.
 struct KeccakLaneCtx {
   int l5, l10, l15, l20;   // lanes of the same column (theta parities)
   int xm1, xp1;            // a lane of column x-1 / x+1 (theta's D)
-  int rot;                 // rho rotation of THIS lane's value before it leaves
+  int cm0, cp0;            // the row-0 lane of column x-1 / x+1 (shared-memory path)
+  int rot;                 // rho rotation of THIS lane's value before it leaves (mod 32)
+  bool swap;               // rho rotation >= 32: exchange the halves first
   int s0, s1, s2;          // rho + pi + chi in one stage: the lanes whose rotated values become B[x, y], B[x+1, y], B[x+2, y]
 };
 
@@ -286,70 +296,101 @@ __device__ __forceinline__ KeccakLaneCtx keccak_lane_ctx(int lane) {
   KeccakLaneCtx c;
   const int l = lane < 25 ? lane : 0, x = l % 5, y = l / 5;
   c.l5 = (l + 5) % 25; c.l10 = (l + 10) % 25; c.l15 = (l + 15) % 25; c.l20 = (l + 20) % 25;
-  c.xm1 = (x + 4) % 5 + 5 * y; c.xp1 = (x + 1) % 5 + 5 * y;
-  c.rot = kRot[l];
+  c.cm0 = (x + 4) % 5; c.cp0 = (x + 1) % 5;
+  c.xm1 = c.cm0 + 5 * y; c.xp1 = c.cp0 + 5 * y;
+  c.rot = kRot[l] & 31; c.swap = kRot[l] >= 32;
   // pi: B[y', 2x' + 3y'] = A[x', y'];  lane (X, Y) receives from the (x', y') with y' = X, 2x' + 3y' = Y (mod 5);
-  // chi reads B[x+1, y] and B[x+2, y] as well: fetch all three straight from their pre-pi lanes (one shuffle stage
-  // instead of the permuting shuffle followed by chi's two)
+  // chi reads B[x+1, y] and B[x+2, y] as well: fetch all three straight from their pre-pi lanes (one exchange stage
+  // instead of the permuting exchange followed by chi's two)
   auto pi_src = [](int X, int Y) { const int yp = X, xp = ((Y - 3 * yp) % 5 + 5) * 3 % 5; return xp + 5 * yp; };   // 2^-1 = 3 (mod 5)
   c.s0 = pi_src(x, y); c.s1 = pi_src((x + 1) % 5, y); c.s2 = pi_src((x + 2) % 5, y);
   return c;
 }
 
-__device__ __forceinline__ uint64_t keccak_f1600_warp(uint64_t a, const KeccakLaneCtx& c, int lane) {
+// rho on the two halves: optional swap (rotation >= 32), then two funnel shifts by rot mod 32
+__device__ __forceinline__ uint64_t keccak_lane_rho(uint64_t a, const KeccakLaneCtx& c) {
+  uint32_t lo = (uint32_t)a, hi = (uint32_t)(a >> 32);
+  const uint32_t l2 = c.swap ? hi : lo, h2 = c.swap ? lo : hi;
+  const uint32_t nh = __funnelshift_l(l2, h2, c.rot), nl = __funnelshift_l(h2, l2, c.rot);
+  return ((uint64_t)nh << 32) | nl;
+}
+
+// sA, sB: this warp's two 32-lane exchange arrays (shared-memory path only)
+template <bool SMEM>
+__device__ __forceinline__ uint64_t keccak_f1600_warp(uint64_t a, const KeccakLaneCtx& c, int lane, uint64_t* sA,
+                                                      uint64_t* sB) {
 #pragma unroll 1
   for (int rnd = 0; rnd < 24; rnd++) {
+    const uint64_t rc = lane == 0 ? kRC[rnd] : 0;
+    uint64_t cm, cp;
     // theta
-    const uint64_t col = a ^ shfl64(a, c.l5) ^ shfl64(a, c.l10) ^ shfl64(a, c.l15) ^ shfl64(a, c.l20);
-    const uint64_t cm = shfl64(col, c.xm1), cp = shfl64(col, c.xp1);
+    if constexpr (SMEM) {
+      sA[lane] = a;
+      __syncwarp();
+      cm = sA[c.cm0] ^ sA[c.cm0 + 5] ^ sA[c.cm0 + 10] ^ sA[c.cm0 + 15] ^ sA[c.cm0 + 20];
+      cp = sA[c.cp0] ^ sA[c.cp0 + 5] ^ sA[c.cp0 + 10] ^ sA[c.cp0 + 15] ^ sA[c.cp0 + 20];
+    } else {
+      const uint64_t col = a ^ shfl64(a, c.l5) ^ shfl64(a, c.l10) ^ shfl64(a, c.l15) ^ shfl64(a, c.l20);
+      cm = shfl64(col, c.xm1); cp = shfl64(col, c.xp1);
+    }
     a ^= cm ^ ((cp << 1) | (cp >> 63));
-    // rho (rotate own value), then pi and chi's operands as three independent shuffles of the rotated lanes
-    const uint64_t r = c.rot ? ((a << c.rot) | (a >> (64 - c.rot))) : a;
-    const uint64_t b = shfl64(r, c.s0), b1 = shfl64(r, c.s1), b2 = shfl64(r, c.s2);
-    a = b ^ (~b1 & b2);
-    if (lane == 0) a ^= kRC[rnd];
+    // rho (rotate own value), then pi and chi's operands as three independent fetches of the rotated lanes
+    const uint64_t r = keccak_lane_rho(a, c);
+    uint64_t b, b1, b2;
+    if constexpr (SMEM) {
+      sB[lane] = r;
+      __syncwarp();
+      b = sB[c.s0]; b1 = sB[c.s1]; b2 = sB[c.s2];
+    } else {
+      b = shfl64(r, c.s0); b1 = shfl64(r, c.s1); b2 = shfl64(r, c.s2);
+    }
+    a = b ^ (~b1 & b2) ^ rc;
   }
   return a;
 }
 
-constexpr int KM_WARPS = 4;
 constexpr size_t MERKLE_WARP_MAX = 8192;   // up to here a warp per path fits the machine in one wave (148 SMs x 64 warps)
-__global__ void __launch_bounds__(32 * KM_WARPS) k_merkle_paths_warp(const uint8_t* __restrict__ leaves, size_t leaf_len,
-                                                                      const uint64_t* __restrict__ leaf_siblings,
-                                                                      const uint64_t* __restrict__ auth_paths,
-                                                                      const uint64_t* __restrict__ indexes, unsigned height,
-                                                                      size_t n, const uint64_t* __restrict__ expected_root,
-                                                                      uint64_t* __restrict__ roots_out,
-                                                                      uint8_t* __restrict__ ok_out) {
-  const int lane = threadIdx.x & 31;
-  const size_t i = (size_t)blockIdx.x * KM_WARPS + (threadIdx.x >> 5);
+template <int WARPS, bool SMEM>
+__global__ void __launch_bounds__(32 * WARPS) k_merkle_paths_warp(const uint8_t* __restrict__ leaves, size_t leaf_len,
+                                                                   const uint64_t* __restrict__ leaf_siblings,
+                                                                   const uint64_t* __restrict__ auth_paths,
+                                                                   const uint64_t* __restrict__ indexes, unsigned height,
+                                                                   size_t n, const uint64_t* __restrict__ expected_root,
+                                                                   uint64_t* __restrict__ roots_out,
+                                                                   uint8_t* __restrict__ ok_out) {
+  __shared__ uint64_t sx[SMEM ? WARPS : 1][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t i = (size_t)blockIdx.x * WARPS + warp;
   if (i >= n) return;   // whole warps leave together
+  uint64_t* sA = sx[SMEM ? warp : 0][0];
+  uint64_t* sB = sx[SMEM ? warp : 0][1];
   const KeccakLaneCtx c = keccak_lane_ctx(lane);
   // leaf: Absorb(leaf) block by block (overwrite the rate lanes, permute when more data follows), then the permutation
   // at the head of Squeeze.  leaf_len is a positive multiple of 8 (checked by the entry point).
   uint64_t a = 0;
   const uint64_t* leaf = reinterpret_cast<const uint64_t*>(leaves + i * leaf_len);
   const size_t words = leaf_len / 8;
-  size_t off = 0;
-  while (words - off > (size_t)KECCAK_RATE_LANES) {
-    if (lane < KECCAK_RATE_LANES) a = leaf[off + lane];
-    a = keccak_f1600_warp(a, c, lane);
-    off += KECCAK_RATE_LANES;
-  }
-  if ((size_t)lane < words - off) a = leaf[off + lane];
-  a = keccak_f1600_warp(a, c, lane);
   const uint64_t idx = indexes[i];
   const uint64_t* ap = auth_paths + i * (size_t)(height - 1) * 4;
+  // the next block / sibling is fetched BEFORE the permutation in front of it, so its HBM latency hides behind it
+  uint64_t nxt = (size_t)lane < words && lane < KECCAK_RATE_LANES ? leaf[lane] : 0;
+  size_t off = 0;
+  while (words - off > (size_t)KECCAK_RATE_LANES) {
+    if (lane < KECCAK_RATE_LANES) a = nxt;
+    off += KECCAK_RATE_LANES;
+    nxt = (size_t)lane < words - off && lane < KECCAK_RATE_LANES ? leaf[off + lane] : 0;
+    a = keccak_f1600_warp<SMEM>(a, c, lane, sA, sB);
+  }
+  if ((size_t)lane < words - off) a = nxt;
+  uint64_t sib = (lane < 8 && height > 0) ? leaf_siblings[i * 4 + (lane & 3)] : 0;
+  a = keccak_f1600_warp<SMEM>(a, c, lane, sA, sB);
   for (unsigned level = 0; level < height; level++) {
-    const uint64_t* sp = level == 0 ? leaf_siblings + i * 4 : ap + (size_t)(level - 1) * 4;
     const bool right = (idx >> level) & 1;       // set bit: current node is the right child
     const uint64_t cur = shfl64(a, lane & 3);    // lanes 0..7 see cur[lane & 3]
     uint64_t v = 0;
-    if (lane < 8) {
-      const uint64_t sib = sp[lane & 3];
-      v = ((lane < 4) == right) ? sib : cur;     // left half = sibling iff we are the right child
-    }
-    a = keccak_f1600_warp(v, c, lane);
+    if (lane < 8) v = ((lane < 4) == right) ? sib : cur;   // left half = sibling iff we are the right child
+    if (lane < 8 && level + 1 < height) sib = ap[(size_t)level * 4 + (lane & 3)];
+    a = keccak_f1600_warp<SMEM>(v, c, lane, sA, sB);
   }
   if (roots_out && lane < 4) roots_out[i * 4 + lane] = a;
   if (ok_out) {
@@ -384,8 +425,25 @@ int merkle_paths_device(b200g16_ctx* ctx, const uint8_t* d_leaves, size_t leaf_l
                         const uint64_t* d_expected_root, uint64_t* d_roots, uint8_t* d_ok) {
   if (n == 0) return 0;
   if (n <= MERKLE_WARP_MAX) {   // latency-bound batch (a WHIR round's queries): one warp per path
-    k_merkle_paths_warp<<<(unsigned)((n + KM_WARPS - 1) / KM_WARPS), 32 * KM_WARPS, 0, ctx->stream>>>(
-        d_leaves, leaf_len, d_sib, d_auth, d_idx, height, n, d_expected_root, d_roots, d_ok);
+    // experiment knob (tools/sweep.py --merkle): B200G16_MERKLE_WARP = 10*warps_per_cta + (1: shared memory, 0: shuffles)
+    // Measured (profiles/r02n_merkle_warp_sweep.jsonl, height 20, 512 B leaves): 64..256 paths 0.071 ms with one warp
+    // per CTA exchanging through shared memory (shuffles 0.077, four warps per CTA 0.079 / 0.094); from ~1000 paths the
+    // SMs hold several warps each and two-warp CTAs with shuffles win (1024: 0.090 against 0.095; 4096: 0.190 / 0.314).
+    const char* e = getenv("B200G16_MERKLE_WARP");
+    const int cfg = e ? atoi(e) : (n <= 512 ? 11 : 20);
+#define B200_MERKLE_LAUNCH(W, S)                                                                                     \
+  k_merkle_paths_warp<W, S><<<(unsigned)((n + W - 1) / W), 32 * W, 0, ctx->stream>>>(                                \
+      d_leaves, leaf_len, d_sib, d_auth, d_idx, height, n, d_expected_root, d_roots, d_ok)
+    switch (cfg) {
+      case 10: B200_MERKLE_LAUNCH(1, false); break;
+      case 11: B200_MERKLE_LAUNCH(1, true); break;
+      case 20: B200_MERKLE_LAUNCH(2, false); break;
+      case 21: B200_MERKLE_LAUNCH(2, true); break;
+      case 40: B200_MERKLE_LAUNCH(4, false); break;
+      case 41: B200_MERKLE_LAUNCH(4, true); break;
+      default: return B200G16_ERR_ARG;
+    }
+#undef B200_MERKLE_LAUNCH
     ctx->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(1024) k_scan_top(uint2* __restrict__ tile_sums
   if (t == 0) {
     totals[0] = ca;  // entries
     totals[1] = cb;  // tasks
-    totals[2] = 0;   // heavy-bucket counter
+    totals[2] = 0;   // split-bucket counters (k_tasks)
+    totals[6] = 0;
   }
 }
 
@@ -279,7 +280,10 @@ __global__ void __launch_bounds__(256) k_tasks(const uint32_t* __restrict__ coun
   uint32_t o = task_off[b];
   for (uint32_t t = 0; t < nt; t++) task_bucket[o + t] = b;
   if (nt > 1) atomicMax(&totals[5], nt);  // deepest merge tree needed (k_merge_pass)
-  if (nt > 4) totals[16 + atomicAdd(&totals[2], 1u)] = b;  // more than one first-level sum: finished by k_merge_heavy
+  // more than one first-level sum after k_merge_pass: up to MERGE_FANIN of them are summed by one thread
+  // (k_merge_mid, list at totals + 16), more by one CTA (k_merge_heavy, list at totals + 16 + nb)
+  if (nt > 16) totals[16 + nb + atomicAdd(&totals[6], 1u)] = b;
+  else if (nt > 4) totals[16 + atomicAdd(&totals[2], 1u)] = b;
 }
 
 

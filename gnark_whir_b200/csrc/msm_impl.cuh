@@ -26,6 +26,8 @@
 // ONE bucket set, entries index the table, and the host has no Horner to do.  A following MSM over the
 // same scalars and decomposition can reuse the sorted lists (share_sort: groth16's Bs1 after Bs2).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ec.cuh"
 
@@ -140,8 +142,16 @@ __global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partia
 // additions, 2 * 2^n in total (the running sum's count), and the dependency depth is n additions instead of
 // ~2 * chunk + 1.5 c.  Afterwards A[0] = G and A[2^m] = U_m; k_reduce_weights scales them by 2^m (m doublings,
 // one thread each) and the fan-in-4 sum passes below add the n + 1 terms.
-template <class F>
-__global__ void __launch_bounds__(128) k_reduce_first(const XYZZ<F>* __restrict__ partials,
+// INL: the addition is expanded in place with both operands in registers (like k_accumulate's mixed addition: no stack
+// copy of the accumulator, every load issued up front) instead of the out-of-line routine.  G1 only — the expanded Fp2
+// code does not fit the instruction cache.  Experiment knob: B200G16_REDUCE_INLINE=0/1 (read once).
+inline bool reduce_inline_default() {
+  static const bool v = [] { const char* e = getenv("B200G16_REDUCE_INLINE"); return e ? atoi(e) != 0 : true; }();
+  return v;
+}
+
+template <class F, bool INL>
+__global__ void __launch_bounds__(128, INL ? 4 : 0) k_reduce_first(const XYZZ<F>* __restrict__ partials,
                                                        const uint32_t* __restrict__ counts,
                                                        const uint32_t* __restrict__ task_off, uint32_t Wr, uint32_t nbw,
                                                        XYZZ<F>* __restrict__ A) {
@@ -153,19 +163,25 @@ __global__ void __launch_bounds__(128) k_reduce_first(const XYZZ<F>* __restrict_
   XYZZ<F> lo = counts[first + i] ? partials[task_off[first + i]] : XYZZ<F>::inf();
   const XYZZ<F> hi = counts[first + i + half] ? partials[task_off[first + i + half]] : XYZZ<F>::inf();
   A[first + i + half] = hi;
-  lo.add(hi);
+  if constexpr (INL) lo.add_inline(hi);
+  else lo.add(hi);
   A[first + i] = lo;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_reduce_level(XYZZ<F>* __restrict__ A, uint32_t Wr, uint32_t nbw, uint32_t l) {
+template <class F, bool INL>
+__global__ void __launch_bounds__(128, INL ? 4 : 0) k_reduce_level(XYZZ<F>* __restrict__ A, uint32_t Wr, uint32_t nbw, uint32_t l) {
   const uint32_t s = nbw >> l, per_w = l * s;
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Wr * per_w) return;
   const uint32_t w = g / per_w, r = g % per_w, j = r / s, i = r % s;
   XYZZ<F>* p = A + (size_t)w * nbw + (j ? (nbw >> j) : 0u) + i;
   XYZZ<F> a = p[0];
-  a.add(p[s]);
+  if constexpr (INL) {
+    const XYZZ<F> b = p[s];
+    a.add_inline(b);
+  } else {
+    a.add(p[s]);
+  }
   p[0] = a;
 }
 
@@ -226,16 +242,34 @@ __global__ void __launch_bounds__(REDUCE_TAIL_THREADS) k_reduce_tail(XYZZ<F>* __
   if (t == 0) out[blockIdx.x] = base[0];
 }
 
-// Buckets split into MORE than MERGE_FANIN tasks (k_tasks lists them: 0/1-heavy witnesses, the low buckets a narrow
-// top window piles its digits into): one CTA per listed bucket finishes the merge as a halving tree over the
-// first-level sums (every MERGE_FANIN-th partial), instead of log4(#tasks) grid-wide launches that find nothing to do
-// for every other bucket.  Grid-stride over the list; totals[2] = list length.
+// Buckets split into MORE than MERGE_FANIN tasks have several first-level sums (every MERGE_FANIN-th partial) after
+// k_merge_pass; k_tasks lists them in two classes.
+//   5..16 tasks (a narrow table window at a small size cuts EVERY bucket into ~5 tasks so that the accumulate kernel
+//   has enough threads): one THREAD per listed bucket adds its <= MERGE_FANIN first-level sums;  totals[2] = list length.
+template <class F>
+__global__ void __launch_bounds__(128) k_merge_mid(XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ mid,
+                                                    const uint32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ task_off,
+                                                    const uint32_t* __restrict__ totals) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= totals[2]) return;
+  const uint32_t b = mid[h], seg = totals[4];
+  XYZZ<F>* p = partials + task_off[b];
+  const uint32_t nt = (counts[b] + seg - 1) / seg;
+  XYZZ<F> acc = p[0];
+  for (uint32_t i = MERGE_FANIN; i < nt; i += MERGE_FANIN) acc.add(p[i]);
+  p[0] = acc;
+}
+
+//   more than 16 tasks (0/1-heavy witnesses, the low buckets a narrow top window piles its digits into): one CTA per
+//   listed bucket finishes the merge as a halving tree over the first-level sums, instead of log4(#tasks) grid-wide
+//   launches that find nothing to do for every other bucket.  Grid-stride over the list; totals[6] = list length.
 template <class F>
 __global__ void __launch_bounds__(256) k_merge_heavy(XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ heavy,
                                                       const uint32_t* __restrict__ counts,
                                                       const uint32_t* __restrict__ task_off,
                                                       const uint32_t* __restrict__ totals) {
-  const uint32_t nheavy = totals[2], seg = totals[4];
+  const uint32_t nheavy = totals[6], seg = totals[4];
   for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
     const uint32_t b = heavy[h];
     XYZZ<F>* p = partials + task_off[b];
@@ -329,8 +363,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   const int spar = reuse ? ls.par : par;  // set holding the sorted state: counts, offsets, tasks, totals
   B200_TRY(ws.digits.ensure(m_max * sizeof(int32_t)));
   B200_TRY(ws.entries.ensure(m_max * sizeof(uint32_t)));
-  // totals[16] + heavy list[nb] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
-  const size_t scan_off = (64 + (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
+  // totals[16] + two lists of split buckets [nb each] + scan tile sums (uint2 per 2048 buckets, 8-byte aligned)
+  const size_t scan_off = (64 + 2 * (size_t)cfg.nb * sizeof(uint32_t) + 7) & ~(size_t)7;
   // every rotating set is sized for this call at once: a prove alternates G1 and G2 MSMs over the sets, and
   // growing a set later would cost a cudaFree (device-wide synchronisation) in the middle of a prove
   for (int q = 0; q < MSM_SETS; q++) {
@@ -358,7 +392,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   uint32_t* entries = ws.entries.as<uint32_t>();
   uint32_t* task_bucket = ws.tasks[spar].as<uint32_t>();
   uint32_t* task_order = task_bucket + max_tasks;
-  uint32_t* heavy = totals + 16;   // list of buckets split into more than MERGE_FANIN tasks (k_tasks), nb entries reserved
+  uint32_t* mid = totals + 16;     // buckets split into 5..16 tasks (k_tasks), nb entries reserved
+  uint32_t* heavy = mid + cfg.nb;  // buckets split into more than 16 tasks, nb entries reserved
   XYZZ<F>* partials = ws.partials[par].as<XYZZ<F>>();
   XYZZ<F>* chunks = ws.chunks[par].as<XYZZ<F>>();
   XYZZ<F>* windows = nullptr;
@@ -425,22 +460,31 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   // dependency chains), so that the next MSM's sort + accumulate on `st` overlap it
   B200_CUDA(cudaEventRecord(ctx->ev_front[par], st));
   B200_CUDA(cudaStreamWaitEvent(tail, ctx->ev_front[par], 0));
-  // split buckets: one grid-wide fan-in-4 pass, then one CTA per bucket that still has more than one first-level sum
+  // split buckets: one grid-wide fan-in-4 pass, then one thread (<= 16 tasks) or one CTA per bucket that still has more
+  // than one first-level sum
   k_merge_pass<F><<<cdiv(max_tasks, 128), 128, 0, tail>>>(partials, task_bucket, counts, task_off, totals, 1u);
+  k_merge_mid<F><<<cdiv(std::min<size_t>(cfg.nb, max_tasks / (MERGE_FANIN + 1) + 1), 128), 128, 0, tail>>>(partials, mid, counts,
+                                                                                                        task_off, totals);
   k_merge_heavy<F><<<(unsigned)ctx->sm_count * 2, 256, 0, tail>>>(partials, heavy, counts, task_off, totals);
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
   const uint32_t nlev = (uint32_t)cfg.c - 1;  // log2(buckets per window)
   uint32_t l0 = 1;                            // first level the one-CTA tail kernel can take
   while (l0 <= nlev && (uint64_t)l0 * (cfg.nbw >> l0) > REDUCE_TAIL_THREADS) l0++;
   if (l0 < 2) l0 = 2;                         // level 1 (reads the partials through the task table) is always its own kernel
-  k_reduce_first<F><<<cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128), 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr,
-                                                                                 cfg.nbw, chunks);
+  constexpr bool CAN_INL = sizeof(F) <= 32;
+  const bool inl = CAN_INL && reduce_inline_default();
+  const unsigned g1 = cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128);
+  if (inl) k_reduce_first<F, CAN_INL><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
+  else k_reduce_first<F, false><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
   int sum_levels = 2;
-  for (uint32_t l = 2; l < l0 && l <= nlev; l++, sum_levels++)
-    k_reduce_level<F><<<cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), 128), 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+  for (uint32_t l = 2; l < l0 && l <= nlev; l++, sum_levels++) {
+    const unsigned gl = cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), 128);
+    if (inl) k_reduce_level<F, CAN_INL><<<gl, 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+    else k_reduce_level<F, false><<<gl, 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+  }
   XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;   // Wr window sums behind the tree
   k_reduce_tail<F><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
-  const int merge_levels = 2;
+  const int merge_levels = 3;
   windows = cur;  // Wr items
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);
   ctx->launches += merge_levels + sum_levels;

@@ -3,7 +3,8 @@ finish these sizes in seconds, except where the C port's closed forms can):
 
   configs[1]  G1 MSM 2^24: result == [sum s_i k_i] G (dot product by the C oracle, one scalar mul),
               and linearity MSM(s) + MSM(t) == MSM(s + t) with s + t formed on the host
-  configs[2]  Fr NTT 2^24: forward/inverse round trips in both conventions, linearity (full-output comparisons
+  configs[2]  Fr NTT 2^24: forward/inverse round trips in both conventions, linearity; 2^26 (the largest size of the sweep):
+              definition check on a sparse input + round trips (full-output comparisons
               of NTT 2^22 / 2^24 and computeH 2^22 against the C port live in test_gpu_bench_sizes.py)
   configs[3]  Keccak: 2^20 Merkle paths, a random sample compared with the C oracle + all roots of paths
               opened from one real tree equal that tree's root
@@ -88,6 +89,38 @@ def test_ntt_2p24_round_trips_and_linearity(ctx):
     Y = bn.fr_from_mont_array(y[idx].cpu().numpy().view(np.uint64))
     S = bn.fr_from_mont_array(s[idx].cpu().numpy().view(np.uint64))
     assert all((p + q) % R == r for p, q, r in zip(X, Y, S))
+
+
+def test_ntt_2p26_largest_size_definition_check_and_round_trips(ctx):
+    """BASELINE.json configs[2] sweeps up to 2^26.  At that size: (1) a sparse input (a handful of nonzero coefficients)
+    makes EVERY output a short closed-form sum, X[k] = sum_t v_t w^(j_t k), which python big ints evaluate exactly for a
+    sample of k — a check against the transform's definition with gnark's DIF output order (bit-reversed); (2) dense
+    round trips in both conventions."""
+    from oracle import ntt as ontt
+    L, n = 26, 1 << 26
+    dom = ontt.Domain(n)
+    rs = np.random.Generator(np.random.PCG64(26))
+    pos = [0, 1, n // 2 + 3, n - 1] + [int(x) for x in rs.integers(0, n, size=4)]
+    vals = [int(x) for x in rs.integers(1, 1 << 62, size=len(pos))]
+    a = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    a[torch.tensor(pos, device="cuda")] = torch.from_numpy(bn.fr_to_mont_array(vals).view(np.int64)).cuda()
+    ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)          # natural in, bit-reversed out
+    ks = [0, 1, 2, n // 2, n - 1] + [int(x) for x in rs.integers(0, n, size=59)]
+    got = bn.fr_from_mont_array(a[torch.tensor([ontt.bitrev(k, L) for k in ks], device="cuda")].cpu().numpy().view(np.uint64))
+    for k, g in zip(ks, got):
+        assert g == sum(v * pow(dom.gen, (j * k) % n, R) for j, v in zip(pos, vals)) % R
+    del a
+    g = torch.Generator(device="cuda").manual_seed(26)
+    a = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+    a[:, 3] &= (1 << 60) - 1
+    ref = a.clone()
+    ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)
+    assert not torch.equal(a, ref)
+    ctx.ntt_dev(a.data_ptr(), L, inverse=True, decimation=lib.DIT)
+    assert torch.equal(a, ref)
+    ctx.ntt_dev(a.data_ptr(), L, coset=True, decimation=lib.DIT)
+    ctx.ntt_dev(a.data_ptr(), L, inverse=True, coset=True, decimation=lib.DIF)
+    assert torch.equal(a, ref)
 
 
 def test_keccak_merkle_2p20_paths(ctx):

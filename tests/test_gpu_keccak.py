@@ -60,6 +60,28 @@ def test_merkle_paths(ctx, height, leaf_len):
     assert not ok2[0] and ok2[1:].all()
 
 
+@pytest.mark.parametrize("cfg", [10, 11, 20, 21, 40, 41])
+def test_merkle_paths_warp_kernel_variants(ctx, monkeypatch, cfg):
+    """The latency kernel (one warp per path) in every shape it can be launched in: 1 / 2 / 4 warps per CTA, lanes
+    exchanged by shuffles (x0) or through shared memory (x1) — all byte-exact against the oracle, including a leaf that
+    ends in a partial block and one that is a whole number of blocks."""
+    monkeypatch.setenv("B200G16_MERKLE_WARP", str(cfg))
+    for height, leaf_len in ((6, 512), (3, 136), (2, 24), (5, 272)):
+        nleaves = 1 << height
+        leaves = [os.urandom(leaf_len) for _ in range(nleaves)]
+        levels = ok.build_merkle_tree(leaves)
+        root = levels[-1][0]
+        L, S, A = [], [], []
+        for i in range(nleaves):
+            sib, ap = ok.merkle_open(levels, i)
+            L.append(np.frombuffer(leaves[i], dtype=np.uint8))
+            S.append(np.frombuffer(sib, dtype=np.uint8))
+            A.append(np.frombuffer(b"".join(ap), dtype=np.uint8).reshape(height - 1, 32))
+        roots, okf = ctx.keccak_merkle_paths(np.stack(L), np.stack(S), np.stack(A).reshape(nleaves, height - 1, 32),
+                                             np.arange(nleaves, dtype=np.uint64), expected_root=root)
+        assert all(bytes(r) == root for r in roots) and okf.all()
+
+
 def test_merkle_paths_prefix_decoded(ctx):
     """Paths arriving in the reference's wire form (prefix-compressed, root-first; mt.go:267-281)."""
     height, leaf_len = 6, 64

@@ -181,6 +181,29 @@ def test_msm_g1_window_table_known_dlog(ctx, rng, mix):
     assert np.array_equal(out, bn.g1_to_array([bn.g1_mul(bn.G1_GEN, sum(k * s for k, s in zip(ks, ss)) % R)])[0])
 
 
+@pytest.mark.parametrize("mix", ["uniform", "whir"])
+@pytest.mark.parametrize("group,logn,c", [(1, 16, 14), (1, 15, 10), (2, 14, 12)])
+def test_msm_narrow_table_every_bucket_split(ctx, rng, group, logn, c, mix):
+    """A narrow table window at a small size cuts EVERY bucket into several tasks (2^16 points, c = 14: ~150 entries per
+    bucket in tasks of 32): the per-thread merge of 5..16 tasks and the per-CTA merge of larger buckets both run."""
+    n = 1 << logn
+    ks = [rng.randrange(1, R) for _ in range(n)]
+    if mix == "uniform":
+        ss = [rng.randrange(R) for _ in range(n)]
+    else:
+        ss = [rng.randrange(2) if (u := rng.random()) < 0.4 else rng.randrange(256) if u < 0.7 else rng.randrange(R)
+              for _ in range(n)]
+    gen = bn.g1_to_array([bn.G1_GEN])[0] if group == 1 else bn.g2_to_array([bn.G2_GEN])[0]
+    bases = ctx.fixed_base_mul(gen, bn.fr_to_mont_array(ks), group=group, resident=True)
+    assert bases.precompute(c) == c
+    out = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    again = ctx.msm(bases, bn.fr_to_mont_array(ss))
+    bases.free()
+    dot = sum(k * s for k, s in zip(ks, ss)) % R
+    exp = bn.g1_to_array([bn.g1_mul(bn.G1_GEN, dot)])[0] if group == 1 else bn.g2_to_array([bn.g2_mul(bn.G2_GEN, dot)])[0]
+    assert np.array_equal(out, exp) and np.array_equal(again, exp)
+
+
 @pytest.mark.parametrize("c", [0, 9])
 def test_msm_g2_window_table(ctx, rng, c):
     n = 1 << 10

@@ -127,6 +127,101 @@ def affine_debug(ctx):
     ctx.set_msm_batch_affine(0, 3, 192)
 
 
+def window_mix_sweep(ctx):
+    """Table window for WITNESS-shaped scalars (40% 0/1, 30% bytes, 30% uniform: the A / B1 / B2 / K MSMs of a prove) next
+    to uniform ones, G1 and G2, c = 15..20 at 2^18..2^22: whole-MSM device time, checked against the closed form."""
+    tbl = torch.from_numpy(g16.fr_array(list(range(256))).view(np.int64)).cuda()
+    arg = [a for a in sys.argv if a.startswith("--logs=")]
+    logs = [int(x) for x in arg[0][7:].split(",")] if arg else [18, 20, 22]
+    for group in (1, 2):
+        gen = g16.g1_point(g16.G1_GEN) if group == 1 else g16.g2_point(g16.G2_GEN)
+        for logn in logs:
+            n = 1 << logn
+            ks = rand_fr(n)
+            d_uni = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+            u = torch.rand(n, device="cuda")
+            sv = torch.randint(0, 256, (n,), device="cuda")
+            d_mix = d_uni.clone()
+            m01, mb = u < 0.4, (u >= 0.4) & (u < 0.7)
+            d_mix[m01] = tbl[sv[m01] & 1]
+            d_mix[mb] = tbl[sv[mb]]
+            want = {}
+            for name, d_sc in (("uniform", d_uni), ("whir_mix", d_mix)):
+                dot = cport.fr_dot(ks, d_sc.cpu().numpy().view(np.uint64))
+                want[name] = cport.g1_gen_mul(dot) if group == 1 else ctx.fixed_base_mul(gen, dot.reshape(1, 4), group=2)[0]
+            for c in range(15, 21):
+                bases = ctx.fixed_base_mul(gen, ks, group=group, resident=True)
+                bases.precompute(c)
+                for name, d_sc in (("uniform", d_uni), ("whir_mix", d_mix)):
+                    best, ok = None, True
+                    for _ in range(4):
+                        ok = ok and bool(np.array_equal(ctx.msm(bases, d_sc.data_ptr(), n=n), want[name]))
+                        ph = ctx.last_timings()
+                        if best is None or sum(ph) < sum(best):
+                            best = ph
+                    emit(config="msm_table_window_mix", group=f"G{group}", log2n=logn, scalars=name, window_bits=c,
+                         adds_per_point=ctx.msm_plan(bases, n)[1], device_ms=round(sum(best), 3),
+                         phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
+                bases.free()
+            del d_uni, d_mix
+
+
+def reduce_ab(ctx):
+    """Bucket-reduction phase of the G1 MSM with a c = 20 table at 2^20 / 2^21 / 2^24 points (uniform scalars); run once
+    with B200G16_REDUCE_INLINE=0 and once with 1 (the knob is read once per process)."""
+    import os
+    gen = g16.g1_point(g16.G1_GEN)
+    for logn in (20, 21, 24):
+        n = 1 << logn
+        ks = rand_fr(n)
+        sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+        want = cport.g1_gen_mul(cport.fr_dot(ks, sc.cpu().numpy().view(np.uint64)))
+        bases = ctx.fixed_base_mul(gen, ks, group=1, resident=True)
+        bases.precompute(20)
+        best, ok = None, True
+        for _ in range(6):
+            ok = ok and bool(np.array_equal(ctx.msm(bases, sc.data_ptr(), n=n), want))
+            ph = ctx.last_timings()
+            if best is None or sum(ph) < sum(best):
+                best = ph
+        emit(config="msm_reduce_ab", reduce_inline=os.environ.get("B200G16_REDUCE_INLINE", "default"), log2n=logn,
+             device_ms=round(sum(best), 3), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
+        bases.free()
+
+
+def merkle_sweep(ctx):
+    """Latency kernel of the Merkle recompute (csrc/keccak.cu k_merkle_paths_warp): warps per CTA x exchange mechanism
+    (B200G16_MERKLE_WARP = 10 * warps + smem) at 64..4096 paths, height 20, 512 B leaves, byte-exact vs the C oracle."""
+    import os
+    from ctypes import c_void_p
+    L = lib.load()
+    height, leaf_len = 20, 512
+    for q in (64, 128, 256, 1024, 4096):
+        leaves = torch.randint(0, 256, (q, leaf_len), dtype=torch.uint8, device="cuda")
+        sib = torch.randint(0, 256, (q, 32), dtype=torch.uint8, device="cuda")
+        auth = torch.randint(0, 256, (q, height - 1, 32), dtype=torch.uint8, device="cuda")
+        idx = torch.randint(0, 1 << 20, (q,), dtype=torch.int64, device="cuda")
+        roots = torch.zeros((q, 32), dtype=torch.uint8, device="cuda")
+        exp = cport.merkle_paths(leaves.cpu().numpy(), sib.cpu().numpy(), auth.cpu().numpy(),
+                                 idx.cpu().numpy().astype(np.uint64))
+
+        def run():
+            lib._check(L.b200g16_keccak_merkle_paths_dev(ctx.h, c_void_p(leaves.data_ptr()), leaf_len,
+                                                         c_void_p(sib.data_ptr()), c_void_p(auth.data_ptr()),
+                                                         c_void_p(idx.data_ptr()), height, q, None,
+                                                         c_void_p(roots.data_ptr()), None))
+        for cfg in (40, 20, 10, 41, 21, 11):
+            os.environ["B200G16_MERKLE_WARP"] = str(cfg)
+            roots.zero_()
+            ms = t_ms(run, reps=10)
+            ok = bool(np.array_equal(roots.cpu().numpy(), exp))
+            # 50 calls enqueued back to back between one pair of events: the kernel's own time without the launch gap
+            ms_train = t_ms(lambda: [run() for _ in range(50)], reps=3) / 50
+            emit(config="keccak_merkle_paths_warp", paths=q, warps_per_cta=cfg // 10, exchange="smem" if cfg % 10 else "shfl",
+                 ms=round(ms, 4), ms_back_to_back=round(ms_train, 4), byte_exact_vs_oracle=ok)
+    os.environ.pop("B200G16_MERKLE_WARP", None)
+
+
 def main():
     global TMAD_PEAK
     big = "--big" in sys.argv
@@ -139,6 +234,18 @@ def main():
         affine_debug(ctx)
         ctx.close()
         return
+    if "--windows-mix" in sys.argv:
+        window_mix_sweep(ctx)
+        ctx.close()
+        return
+    if "--reduce-ab" in sys.argv:
+        reduce_ab(ctx)
+        ctx.close()
+        return
+    if "--merkle" in sys.argv:
+        merkle_sweep(ctx)
+        ctx.close()
+        return
     if "--affine" in sys.argv:
         affine_sweep(ctx)
         ctx.close()
@@ -149,9 +256,11 @@ def main():
     tbl = torch.from_numpy(g16.fr_array(list(range(256))).view(np.int64)).cuda()
 
     # ---- MSM sweeps
+    only_ntt = "--ntt" in sys.argv      # NTT / computeH section alone, up to 2^26
+    big = big or only_ntt
     for group, logs in ((1, [16, 18, 20, 22, 24]), (2, [16, 18, 20, 22])):
         gen = g16.g1_point(g16.G1_GEN) if group == 1 else g16.g2_point(g16.G2_GEN)
-        for logn in logs:
+        for logn in ([] if only_ntt else logs):
             n = 1 << logn
             ks = rand_fr(n)
             bases = ctx.fixed_base_mul(gen, ks, group=group, resident=True)
@@ -205,6 +314,9 @@ def main():
              phases_ms=[round(x, 4) for x in ctx.last_timings()])
         del a, b, c, ref
 
+    if only_ntt:
+        ctx.close()
+        return
     # ---- Keccak
     nk = 1 << 24
     st = torch.randint(0, 1 << 62, (nk, 25), dtype=torch.int64, device="cuda")
