@@ -1,5 +1,6 @@
 // Group-independent front half of the MSM: scalar recoding, histogram, scan, scatter.
 // See msm_impl.cuh for the pipeline overview.
+#include <cstdlib>
 #include "msm_impl.cuh"
 
 namespace b200 {
@@ -296,15 +297,30 @@ __device__ __forceinline__ uint32_t task_len(uint32_t cnt, uint32_t j, uint32_t 
   return rem < seg ? rem : seg;
 }
 
-__global__ void __launch_bounds__(256) k_task_hist(const uint32_t* __restrict__ task_bucket,
-                                                    const uint32_t* __restrict__ counts,
-                                                    const uint32_t* __restrict__ task_off,
-                                                    const uint32_t* __restrict__ totals, uint32_t* __restrict__ hist) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= totals[1]) return;
-  uint32_t b = task_bucket[t];
-  uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
-  atomicAdd(&hist[len < TASK_BINS ? len : TASK_BINS - 1], 1u);
+// Task lengths cluster on a few values (evenly loaded buckets: ~30 distinct lengths; a 0/1-heavy witness: most tasks are
+// exactly `seg` long), so one global atomic per task serialises on a handful of addresses (2^19 tasks: 119 us for the
+// histogram and 121 us for the ordering, profiles/r02j_ncu_launches_bench_2p24.csv).  Both kernels therefore count
+// inside the CTA first (shared-memory histogram, the atomic's return value is the task's rank within the CTA) and touch
+// global memory once per CTA and occupied bin.
+constexpr int TASK_CTA = 1024;
+
+__global__ void __launch_bounds__(TASK_CTA) k_task_hist(const uint32_t* __restrict__ task_bucket,
+                                                         const uint32_t* __restrict__ counts,
+                                                         const uint32_t* __restrict__ task_off,
+                                                         const uint32_t* __restrict__ totals, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[TASK_BINS];
+  if (blockIdx.x * TASK_CTA >= totals[1]) return;   // whole CTA past the last task
+  for (uint32_t b = threadIdx.x; b < TASK_BINS; b += TASK_CTA) h[b] = 0;
+  __syncthreads();
+  const uint32_t t = blockIdx.x * TASK_CTA + threadIdx.x;
+  if (t < totals[1]) {
+    const uint32_t b = task_bucket[t];
+    const uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
+    atomicAdd(&h[len < TASK_BINS ? len : TASK_BINS - 1], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < TASK_BINS; b += TASK_CTA)
+    if (h[b]) atomicAdd(&hist[b], h[b]);
 }
 
 // single CTA, 1024 threads x 4 bins: exclusive scan in DESCENDING length order -> cursor[bin]
@@ -326,16 +342,29 @@ __global__ void __launch_bounds__(1024) k_task_scan(const uint32_t* __restrict__
   for (int k = 0; k < 4; k++) { cursor[TASK_BINS - 1 - (4 * t + k)] = e; e += v[k]; }
 }
 
-__global__ void __launch_bounds__(256) k_task_order(const uint32_t* __restrict__ task_bucket,
-                                                     const uint32_t* __restrict__ counts,
-                                                     const uint32_t* __restrict__ task_off,
-                                                     const uint32_t* __restrict__ totals, uint32_t* __restrict__ cursor,
-                                                     uint32_t* __restrict__ task_order) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= totals[1]) return;
-  uint32_t b = task_bucket[t];
-  uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
-  task_order[atomicAdd(&cursor[len < TASK_BINS ? len : TASK_BINS - 1], 1u)] = t;
+__global__ void __launch_bounds__(TASK_CTA) k_task_order(const uint32_t* __restrict__ task_bucket,
+                                                          const uint32_t* __restrict__ counts,
+                                                          const uint32_t* __restrict__ task_off,
+                                                          const uint32_t* __restrict__ totals, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ task_order) {
+  __shared__ uint32_t h[TASK_BINS];   // per bin: this CTA's count, then the base of its range in task_order
+  if (blockIdx.x * TASK_CTA >= totals[1]) return;
+  for (uint32_t b = threadIdx.x; b < TASK_BINS; b += TASK_CTA) h[b] = 0;
+  __syncthreads();
+  const uint32_t t = blockIdx.x * TASK_CTA + threadIdx.x;
+  uint32_t bin = 0, rank = 0;
+  const bool valid = t < totals[1];
+  if (valid) {
+    const uint32_t b = task_bucket[t];
+    const uint32_t len = task_len(counts[b], t - task_off[b], totals[4]);
+    bin = len < TASK_BINS ? len : TASK_BINS - 1;
+    rank = atomicAdd(&h[bin], 1u);
+  }
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < TASK_BINS; b += TASK_CTA)
+    if (h[b]) h[b] = atomicAdd(&cursor[b], h[b]);
+  __syncthreads();
+  if (valid) task_order[h[bin] + rank] = t;
 }
 
 int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uint32_t n, int32_t* digits,
@@ -344,11 +373,22 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
                    uint32_t* scan_scratch, int* ev) {
   cudaStream_t st = ctx->stream;
   auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
+  // B200G16_SORT_TRACE=1: an event after every operation of this phase, printed (and the stream drained) at its end —
+  // where the phase's time goes inside a real call, launch gaps included (tools/sweep.py --reduce-ab)
+  static const bool trace = getenv("B200G16_SORT_TRACE") != nullptr;
+  static cudaEvent_t tev[16];
+  static bool tev_made = false;
+  int nt = 0;
+  if (trace && !tev_made) { for (auto& e : tev) cudaEventCreate(&e); tev_made = true; }
+  auto tr = [&]() { if (trace && nt < 16) cudaEventRecord(tev[nt++], st); };
   mark();
+  tr();
   B200_CUDA(cudaMemsetAsync(counts, 0, (size_t)cfg.nb * sizeof(uint32_t), st));
   B200_CUDA(cudaMemsetAsync(totals, 0, 16 * sizeof(uint32_t), st));
   k_digits<<<cdiv(n, 256), 256, 0, st>>>(d_scalars, n, cfg.c, cfg.W, cfg.bstride, digits, counts, totals);
+  tr();
   k_pick_seg<<<1, 1, 0, st>>>(totals, cfg.nb, cfg.target_tasks);
+  tr();
   mark();
   const uint32_t ntiles = cdiv(cfg.nb, SCAN_TILE);
   uint2* tile_sums = reinterpret_cast<uint2*>(scan_scratch);
@@ -357,13 +397,30 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   k_scan_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums);
   k_scan_top<<<1, 1024, 0, st>>>(tile_sums, ntiles, totals);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts, cfg.nb, totals, tile_sums, offsets, cursor, task_off);
+  tr();
   k_scatter<<<dim3(cdiv(n, 256), cfg.W), 256, 0, st>>>(digits, n, cfg.bstride, cfg.ent_stride, cfg.ent_off, cursor, entries);
+  tr();
   k_tasks<<<cdiv(cfg.nb, 256), 256, 0, st>>>(counts, task_off, cfg.nb, totals, task_bucket);
+  tr();
   B200_CUDA(cudaMemsetAsync(hist, 0, TASK_BINS * sizeof(uint32_t), st));
-  k_task_hist<<<cdiv(max_tasks, 256), 256, 0, st>>>(task_bucket, counts, task_off, totals, hist);
+  k_task_hist<<<cdiv(max_tasks, TASK_CTA), TASK_CTA, 0, st>>>(task_bucket, counts, task_off, totals, hist);
+  tr();
   k_task_scan<<<1, 1024, 0, st>>>(hist, hist_cursor);
-  k_task_order<<<cdiv(max_tasks, 256), 256, 0, st>>>(task_bucket, counts, task_off, totals, hist_cursor, task_order);
+  k_task_order<<<cdiv(max_tasks, TASK_CTA), TASK_CTA, 0, st>>>(task_bucket, counts, task_off, totals, hist_cursor, task_order);
+  tr();
   mark();
+  if (trace) {
+    cudaStreamSynchronize(st);
+    static const char* what[] = {"memsets + k_digits", "k_pick_seg", "scan x3", "k_scatter", "k_tasks", "memset + k_task_hist",
+                                 "k_task_scan + k_task_order"};
+    fprintf(stderr, "[sort trace n=%u c=%d]", n, cfg.c);
+    for (int i = 0; i + 1 < nt; i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      fprintf(stderr, "  %s %.1f us", what[i], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+  }
   ctx->launches += 10;
   B200_CUDA(cudaGetLastError());
   return 0;

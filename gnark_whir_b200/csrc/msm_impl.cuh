@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partia
 // INL: the addition is expanded in place with both operands in registers (like k_accumulate's mixed addition: no stack
 // copy of the accumulator, every load issued up front) instead of the out-of-line routine.  G1 only — the expanded Fp2
 // code does not fit the instruction cache.  Experiment knob: B200G16_REDUCE_INLINE=0/1 (read once).
-inline bool reduce_inline_default() {
-  static const bool v = [] { const char* e = getenv("B200G16_REDUCE_INLINE"); return e ? atoi(e) != 0 : true; }();
+inline int reduce_inline_default() {   // 0: out of line, 1: the grid-wide levels, 2: also the one-CTA tail
+  static const int v = [] { const char* e = getenv("B200G16_REDUCE_INLINE"); return e ? atoi(e) : 2; }();
   return v;
 }
 
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(32) k_reduce_weights(const XYZZ<F>* __restrict
 // sum passes before: profiles/r02f_ncu_launches_bench_2p24.csv).
 constexpr uint32_t REDUCE_TAIL_THREADS = 512;   // <= 128 registers per thread: the XYZZ addition keeps ~95 live
 
-template <class F>
+template <class F, bool INL>
 __global__ void __launch_bounds__(REDUCE_TAIL_THREADS) k_reduce_tail(XYZZ<F>* __restrict__ A, uint32_t nbw, uint32_t n,
                                                                        uint32_t l0, XYZZ<F>* __restrict__ out) {
   XYZZ<F>* base = A + (size_t)blockIdx.x * nbw;
@@ -215,7 +215,12 @@ __global__ void __launch_bounds__(REDUCE_TAIL_THREADS) k_reduce_tail(XYZZ<F>* __
       const uint32_t j = t / s, i = t % s;
       XYZZ<F>* p = base + (j ? (nbw >> j) : 0u) + i;
       XYZZ<F> a = p[0];
-      a.add(p[s]);
+      if constexpr (INL) {
+        const XYZZ<F> b = p[s];
+        a.add_inline(b);
+      } else {
+        a.add(p[s]);
+      }
       p[0] = a;
     }
     __syncthreads();
@@ -233,7 +238,12 @@ __global__ void __launch_bounds__(REDUCE_TAIL_THREADS) k_reduce_tail(XYZZ<F>* __
     const uint32_t half = (len + 1) >> 1;
     if (t < len - half) {
       XYZZ<F> a = *slot(t);
-      a.add(*slot(t + half));
+      if constexpr (INL) {
+        const XYZZ<F> b = *slot(t + half);
+        a.add_inline(b);
+      } else {
+        a.add(*slot(t + half));
+      }
       *slot(t) = a;
     }
     __syncthreads();
@@ -472,7 +482,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   while (l0 <= nlev && (uint64_t)l0 * (cfg.nbw >> l0) > REDUCE_TAIL_THREADS) l0++;
   if (l0 < 2) l0 = 2;                         // level 1 (reads the partials through the task table) is always its own kernel
   constexpr bool CAN_INL = sizeof(F) <= 32;
-  const bool inl = CAN_INL && reduce_inline_default();
+  const bool inl = CAN_INL && reduce_inline_default() >= 1, inl_tail = CAN_INL && reduce_inline_default() >= 2;
   const unsigned g1 = cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128);
   if (inl) k_reduce_first<F, CAN_INL><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
   else k_reduce_first<F, false><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
@@ -483,7 +493,8 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
     else k_reduce_level<F, false><<<gl, 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
   }
   XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;   // Wr window sums behind the tree
-  k_reduce_tail<F><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
+  if (inl_tail) k_reduce_tail<F, CAN_INL><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
+  else k_reduce_tail<F, false><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
   const int merge_levels = 3;
   windows = cur;  // Wr items
   if (record_events && ev < 18) cudaEventRecord(ctx->ev[ev++], tail);

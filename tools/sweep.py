@@ -171,7 +171,8 @@ def reduce_ab(ctx):
     with B200G16_REDUCE_INLINE=0 and once with 1 (the knob is read once per process)."""
     import os
     gen = g16.g1_point(g16.G1_GEN)
-    for logn in (20, 21, 24):
+    arg = [a for a in sys.argv if a.startswith("--logs=")]
+    for logn in ([int(x) for x in arg[0][7:].split(",")] if arg else (20, 21, 24)):
         n = 1 << logn
         ks = rand_fr(n)
         sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
