@@ -238,6 +238,7 @@ int b200g16_init(int device, b200g16_ctx** out) {
   }
   B200_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : ctx->ev_copy) B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : ctx->ev_slot) B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : ctx->ev) B200_CUDA(cudaEventCreate(&ev));
   for (int i = 0; i < MSM_SETS; i++) {
     B200_CUDA(cudaEventCreateWithFlags(&ctx->ev_front[i], cudaEventDisableTiming));
@@ -268,6 +269,7 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   for (auto& ev : ctx->ev) cudaEventDestroy(ev);
   for (int i = 0; i < MSM_SETS; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
   for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_slot) cudaEventDestroy(ev);
   h2d_stager_release(ctx);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->tail_stream);

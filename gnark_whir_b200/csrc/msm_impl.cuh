@@ -328,7 +328,7 @@ constexpr size_t AFF_AUTO_MIN_ENTRIES = (size_t)40 << 20;
 // Window table attached to a bases vector (b200g16_bases_precompute): row k holds 2^(c k) * P_i, so
 // digit k of scalar i addresses entry k * stride + i and ALL windows accumulate into one bucket set.
 // (struct MsmTable lives in common.cuh)
-constexpr int MSM_SLOTS = 8;           // independent result slots (a prove enqueues 5 MSMs back to back)
+constexpr int MSM_SLOTS = 8;           // independent result slots (a prove enqueues 5 MSMs back to back); ctx->ev_slot has as many
 constexpr int MSM_MAX_WINDOWS = 130;
 
 // Enqueue one MSM on ctx->stream; its W window sums land in pinned slot `slot` once the stream
@@ -483,14 +483,18 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   if (l0 < 2) l0 = 2;                         // level 1 (reads the partials through the task table) is always its own kernel
   constexpr bool CAN_INL = sizeof(F) <= 32;
   const bool inl = CAN_INL && reduce_inline_default() >= 1, inl_tail = CAN_INL && reduce_inline_default() >= 2;
-  const unsigned g1 = cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), 128);
-  if (inl) k_reduce_first<F, CAN_INL><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
-  else k_reduce_first<F, false><<<g1, 128, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
+  // CTA size of the grid-wide levels.  G2 (~180 registers per thread, the out-of-line addition): experiment knob
+  // B200G16_G2_REDUCE_BLOCK (read once)
+  static const unsigned g2_block = [] { const char* e = getenv("B200G16_G2_REDUCE_BLOCK"); return e ? (unsigned)atoi(e) : 128u; }();
+  const unsigned rb = CAN_INL ? 128u : g2_block;
+  const unsigned g1 = cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), rb);
+  if (inl) k_reduce_first<F, CAN_INL><<<g1, rb, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
+  else k_reduce_first<F, false><<<g1, rb, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
   int sum_levels = 2;
   for (uint32_t l = 2; l < l0 && l <= nlev; l++, sum_levels++) {
-    const unsigned gl = cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), 128);
-    if (inl) k_reduce_level<F, CAN_INL><<<gl, 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
-    else k_reduce_level<F, false><<<gl, 128, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+    const unsigned gl = cdiv((size_t)cfg.Wr * l * (cfg.nbw >> l), rb);
+    if (inl) k_reduce_level<F, CAN_INL><<<gl, rb, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
+    else k_reduce_level<F, false><<<gl, rb, 0, tail>>>(chunks, (uint32_t)cfg.Wr, cfg.nbw, l);
   }
   XYZZ<F>* cur = chunks + (size_t)cfg.Wr * cfg.nbw;   // Wr window sums behind the tree
   if (inl_tail) k_reduce_tail<F, CAN_INL><<<(unsigned)cfg.Wr, REDUCE_TAIL_THREADS, 0, tail>>>(chunks, cfg.nbw, nlev, l0 > nlev ? nlev + 1 : l0, cur);
@@ -503,6 +507,7 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   B200_CUDA(cudaMemcpyAsync((char*)ws.pinned + (size_t)slot * slot_bytes, windows, (size_t)cfg.Wr * sizeof(XYZZ<F>),
                             cudaMemcpyDeviceToHost, tail));
   B200_CUDA(cudaEventRecord(ctx->ev_tail[par], tail));
+  B200_CUDA(cudaEventRecord(ctx->ev_slot[slot], tail));
   ctx->tail_pending[par] = true;
   if (record_events) ctx->timings.n = -(ev - 1);  // negative: events recorded, not yet resolved
   *cfg_out = cfg;

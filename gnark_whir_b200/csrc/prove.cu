@@ -225,24 +225,43 @@ int prove_back(b200g16_ctx* ctx, const b200g16_pk* pk, const Fr* d_h, const Fr& 
   B200_TRY(prove_enqueue_one(ctx, pk, 3, d_h + pk->off_z, pk->n_z, &ctx->prove_cfg[3]));
   if (ev < 18) cudaEventRecord(ctx->ev[ev++], st);
   B200_TRY(msm_join(ctx));
-  DeltaMultiples dm;
-  if (!pk->partial) dm = delta_multiples(pk, r, s);  // host work hidden behind the GPU's
-  B200_CUDA(cudaStreamSynchronize(st));
-  *ev_io = ev;
   const MsmCfg* cfg = ctx->prove_cfg;
-
   G1Affine A, B1, K, Z;
   G2Affine B2;
-  B200_TRY(msm_collect<Fp>(ctx, 0, cfg[0], &A));
-  B200_TRY(msm_collect<Fp>(ctx, 1, cfg[1], &B1));
-  B200_TRY(msm_collect<Fp>(ctx, 2, cfg[2], &K));
-  B200_TRY(msm_collect<Fp>(ctx, 3, cfg[3], &Z));
-  B200_TRY(msm_collect<Fp2>(ctx, 4, cfg[4], &B2));
-
   memset(out, 0, sizeof(*out));
   if (!pk->partial) {
-    prove_finish_host(pk, dm, A, B1, K, Z, B2, r, s, out);
+    // Host work under the GPU's: the delta multiples first, then every result is taken the moment ITS window sums have
+    // landed (ev_slot) — Ar, s*Ar, Bs1, r*Bs1 and Bs (0.5 ms of host scalar multiplications and inversions) are done
+    // while K, computeH and Z still run; after the last synchronisation only two normalisations and one sum are left.
+    DeltaMultiples dm = delta_multiples(pk, r, s);
+    B200_CUDA(cudaEventSynchronize(ctx->ev_slot[4]));   // the tails finish in enqueue order: B2, B1, A, K, Z
+    B200_TRY(msm_collect<Fp2>(ctx, 4, cfg[4], &B2));
+    const G2Affine bs = host_sum<Fp2>({B2, pk->beta2, dm.s_delta2});
+    B200_CUDA(cudaEventSynchronize(ctx->ev_slot[1]));
+    B200_TRY(msm_collect<Fp>(ctx, 1, cfg[1], &B1));
+    const G1Affine bs1 = host_sum<Fp>({B1, pk->beta, dm.s_delta});
+    const G1Affine r_bs1 = host_scalar_mul_aff<Fp>(bs1, r);
+    B200_CUDA(cudaEventSynchronize(ctx->ev_slot[0]));
+    B200_TRY(msm_collect<Fp>(ctx, 0, cfg[0], &A));
+    const G1Affine ar = host_sum<Fp>({A, pk->alpha, dm.r_delta});
+    const G1Affine s_ar = host_scalar_mul_aff<Fp>(ar, s);
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_TRY(msm_collect<Fp>(ctx, 2, cfg[2], &K));
+    B200_TRY(msm_collect<Fp>(ctx, 3, cfg[3], &Z));
+    const G1Affine krs = host_sum<Fp>({K, Z, dm.kr_delta, s_ar, r_bs1});
+    memcpy(out->ar, &ar, 64);
+    memcpy(out->bs, &bs, 128);
+    memcpy(out->krs, &krs, 64);
+    memcpy(out->bs1, &bs1, 64);
+  } else {
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_TRY(msm_collect<Fp>(ctx, 0, cfg[0], &A));
+    B200_TRY(msm_collect<Fp>(ctx, 1, cfg[1], &B1));
+    B200_TRY(msm_collect<Fp>(ctx, 2, cfg[2], &K));
+    B200_TRY(msm_collect<Fp>(ctx, 3, cfg[3], &Z));
+    B200_TRY(msm_collect<Fp2>(ctx, 4, cfg[4], &B2));
   }
+  *ev_io = ev;
   memcpy(out->msm_a, &A, 64);
   memcpy(out->msm_b1, &B1, 64);
   memcpy(out->msm_k, &K, 64);

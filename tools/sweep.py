@@ -170,14 +170,16 @@ def reduce_ab(ctx):
     """Bucket-reduction phase of the G1 MSM with a c = 20 table at 2^20 / 2^21 / 2^24 points (uniform scalars); run once
     with B200G16_REDUCE_INLINE=0 and once with 1 (the knob is read once per process)."""
     import os
-    gen = g16.g1_point(g16.G1_GEN)
+    g2 = "--g2" in sys.argv
+    gen = g16.g2_point(g16.G2_GEN) if g2 else g16.g1_point(g16.G1_GEN)
     arg = [a for a in sys.argv if a.startswith("--logs=")]
     for logn in ([int(x) for x in arg[0][7:].split(",")] if arg else (20, 21, 24)):
         n = 1 << logn
         ks = rand_fr(n)
         sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
-        want = cport.g1_gen_mul(cport.fr_dot(ks, sc.cpu().numpy().view(np.uint64)))
-        bases = ctx.fixed_base_mul(gen, ks, group=1, resident=True)
+        dot = cport.fr_dot(ks, sc.cpu().numpy().view(np.uint64))
+        want = ctx.fixed_base_mul(gen, dot.reshape(1, 4), group=2)[0] if g2 else cport.g1_gen_mul(dot)
+        bases = ctx.fixed_base_mul(gen, ks, group=2 if g2 else 1, resident=True)
         bases.precompute(20)
         best, ok = None, True
         for _ in range(6):
@@ -185,7 +187,8 @@ def reduce_ab(ctx):
             ph = ctx.last_timings()
             if best is None or sum(ph) < sum(best):
                 best = ph
-        emit(config="msm_reduce_ab", reduce_inline=os.environ.get("B200G16_REDUCE_INLINE", "default"), log2n=logn,
+        emit(config="msm_reduce_ab", group="G2" if g2 else "G1", reduce_inline=os.environ.get("B200G16_REDUCE_INLINE", "default"),
+             g2_reduce_block=os.environ.get("B200G16_G2_REDUCE_BLOCK", "default"), log2n=logn,
              device_ms=round(sum(best), 3), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
         bases.free()
 
