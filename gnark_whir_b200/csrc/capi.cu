@@ -259,6 +259,7 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   for (int i = 0; i < MSM_SETS; i++)
     for (DevBuf* b : {&ctx->msm.counts[i], &ctx->msm.partials[i], &ctx->msm.chunks[i], &ctx->msm.misc[i], &ctx->msm.tasks[i]})
       bufs.push_back(b);
+  for (auto& b : ctx->async_scalars) bufs.push_back(&b);
   for (DevBuf* b : bufs) b->release();
   for (int v = 0; v < 3; v++) {
     for (int d = 0; d < 8; d++)
@@ -399,6 +400,60 @@ int b200g16_msm_g1_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offs
 int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const void* d_scalars, size_t n,
                        uint64_t out[16]) {
   return msm_entry<Fp2>(ctx, bases, 2, offset, d_scalars, true, n, out);
+}
+
+// ---- asynchronous G1 MSM: enqueue now, take the result later.  gnark runs pedersen.ProveKnowledge after Solve and
+// before the five MSMs of Prove; nothing in between depends on its result, so a host can enqueue it, call
+// b200g16_prove, and collect it afterwards — its sort and accumulate run first, its bucket reduction hides under the
+// prove's first MSM, and no synchronisation of its own is paid.
+constexpr int ASYNC_FIRST_SLOT = 5;   // a prove owns slots 0..4, a pipelined host-scalar MSM 0..3
+static int msm_begin(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const void* scalars, bool on_device,
+                     size_t n, int* ticket) {
+  if (!ctx || !bases || !ticket || (n && !scalars)) return fail(B200G16_ERR_ARG, "msm_begin: null argument");
+  if (bases->group != 1) return fail(B200G16_ERR_ARG, "msm_begin: G1 bases expected");
+  if (bases->device != ctx->device) return fail(B200G16_ERR_STATE, "msm_begin: bases live on another device");
+  if (offset > bases->n || n > bases->n - offset)
+    return fail(B200G16_ERR_ARG, "msm_begin: range [%zu,%zu) exceeds %zu bases", offset, offset + n, bases->n);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (ctx->prove_active) return fail(B200G16_ERR_STATE, "msm_begin: a prove is open on this ctx");
+  int t = 0;
+  while (t < 3 && ctx->async_open[t]) t++;
+  if (t == 3) return fail(B200G16_ERR_STATE, "msm_begin: all three tickets are open (b200g16_msm_g1_end releases one)");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  const Fr* d_scalars = reinterpret_cast<const Fr*>(scalars);
+  if (!on_device && n) {
+    B200_TRY(ctx->async_scalars[t].ensure(n * sizeof(Fr)));
+    B200_TRY(h2d_copy(ctx, ctx->async_scalars[t].p, scalars, n * sizeof(Fr), ctx->stream));
+    d_scalars = ctx->async_scalars[t].as<Fr>();
+  }
+  MsmTable tab;
+  const MsmTable* tp = nullptr;
+  const Affine<Fp>* pts = msm_operand<Fp>(bases, offset, &tab, &tp);
+  B200_TRY(msm_enqueue<Fp>(ctx, pts, tp, d_scalars, n, ASYNC_FIRST_SLOT + t, &ctx->async_cfg[t], false));
+  ctx->async_open[t] = true;
+  *ticket = t;
+  return 0;
+}
+
+int b200g16_msm_g1_begin(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const uint64_t* scalars, size_t n,
+                         int* ticket) {
+  return msm_begin(ctx, bases, offset, scalars, false, n, ticket);
+}
+int b200g16_msm_g1_begin_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                             int* ticket) {
+  return msm_begin(ctx, bases, offset, d_scalars, true, n, ticket);
+}
+int b200g16_msm_g1_end(b200g16_ctx* ctx, int ticket, uint64_t out[8]) {
+  if (!ctx || !out || ticket < 0 || ticket >= 3) return fail(B200G16_ERR_ARG, "msm_end: bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (!ctx->async_open[ticket]) return fail(B200G16_ERR_STATE, "msm_end: ticket %d is not open", ticket);
+  B200_CUDA(cudaSetDevice(ctx->device));
+  ctx->async_open[ticket] = false;
+  if (ctx->async_cfg[ticket].W) B200_CUDA(cudaEventSynchronize(ctx->ev_slot[ASYNC_FIRST_SLOT + ticket]));
+  Affine<Fp> res;
+  B200_TRY(msm_collect<Fp>(ctx, ASYNC_FIRST_SLOT + ticket, ctx->async_cfg[ticket], &res));
+  memcpy(out, &res, sizeof(res));
+  return 0;
 }
 
 int b200g16_ntt_dev(b200g16_ctx* ctx, void* d_data, unsigned log2n, unsigned batch, int inverse, int coset,

@@ -161,6 +161,10 @@ struct b200g16_ctx {
   b200::MsmSorted last_sort;
   // a prove between its two halves (b200g16_prove_begin_dev / _end_dev): decompositions of the five MSMs
   b200::MsmCfg prove_cfg[5] = {};
+  // b200g16_msm_g1_begin*/_end: result slots 5..7 (a prove owns 0..4), one cfg and one scalar buffer per ticket
+  b200::MsmCfg async_cfg[3] = {};
+  bool async_open[3] = {};
+  b200::DevBuf async_scalars[3];
   const struct b200g16_pk* prove_pk = nullptr;
   bool prove_active = false;
   int sort_reader[b200::MSM_SETS] = {-1, -1, -1};  // sort_reader[p] = set of an MSM whose tail still reads sorted set p (shared)

@@ -523,13 +523,16 @@ def Prove(ctx, r1cs, pk, witness, r=None, s=None, resolve=None, want_h=False):
         w[r1cs.commitment_wire] = commitment_challenge(com, [w[i] for i in r1cs.public_committed])
         if resolve is not None:
             resolve(w)
-        pok = ctx.msm(ck.basis_exp_sigma_dev, vals)              # pedersen ProveKnowledge (1 commitment: fold = id)
+        # pedersen ProveKnowledge (1 commitment: fold = id): enqueued now, collected after the prove's own MSMs
+        pok_ticket = ctx.msm_begin(ck.basis_exp_sigma_dev, vals)
         proof_commitments = [com]
     a, b, c = solve_abc(r1cs, w)
     r = secrets.randbelow(R_MOD) if r is None else r
     s = secrets.randbelow(R_MOD) if s is None else s
     out, h = ctx.prove(pk.device_handle(ctx), fr_array(w), fr_array(a), fr_array(b), fr_array(c),
                        fr_array([r])[0], fr_array([s])[0], want_h=want_h, log2_domain=pk.log2_domain)
+    if r1cs.commitment_wire >= 0:
+        pok = ctx.msm_end(pok_ticket)
     dbg = dict(out)
     dbg["h"] = h
     dbg["witness"] = w

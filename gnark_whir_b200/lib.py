@@ -55,6 +55,9 @@ SIGNATURES = {
     "b200g16_msm_g1": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g2": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_msm_g1_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "b200g16_msm_g1_begin": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(C.c_int)]),
+    "b200g16_msm_g1_begin_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, C.POINTER(C.c_int)]),
+    "b200g16_msm_g1_end": (C.c_int, [_vp, C.c_int, _vp]),
     "b200g16_msm_g2_dev": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "b200g16_ntt": (C.c_int, [_vp, _vp, C.c_uint, C.c_int, C.c_int, C.c_int]),
     "b200g16_ntt_dev": (C.c_int, [_vp, _vp, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]),
@@ -661,4 +664,24 @@ class Context:
         else:  # raw device pointer (e.g. torch tensor .data_ptr())
             fn = lib.b200g16_msm_g1_dev if bases.group == 1 else lib.b200g16_msm_g2_dev
             _check(fn(self.h, bases.handle, offset, _vp(int(scalars)), n, _ptr(out)))
+        return out
+
+    def msm_begin(self, bases, scalars, offset=0, n=None):
+        """Enqueue a G1 MSM (b200g16_msm_g1_begin / _begin_dev) and return its ticket; msm_end(ticket) collects the
+        result.  Calls made in between run behind it.  The scalars must stay alive and unchanged until msm_end."""
+        lib, ticket = load(), C.c_int(-1)
+        if isinstance(scalars, np.ndarray):
+            sc = _u64(scalars, 4)
+            n = sc.shape[0] if n is None else n
+            _check(lib.b200g16_msm_g1_begin(self.h, bases.handle, offset, _ptr(sc), n, C.byref(ticket)))
+            self._async_keep = getattr(self, "_async_keep", {})
+            self._async_keep[ticket.value] = sc
+        else:
+            _check(lib.b200g16_msm_g1_begin_dev(self.h, bases.handle, offset, _vp(int(scalars)), n, C.byref(ticket)))
+        return ticket.value
+
+    def msm_end(self, ticket):
+        out = np.zeros(8, dtype=np.uint64)
+        _check(load().b200g16_msm_g1_end(self.h, int(ticket), _ptr(out)))
+        getattr(self, "_async_keep", {}).pop(int(ticket), None)
         return out

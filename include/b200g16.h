@@ -207,6 +207,18 @@ int b200g16_msm_g1_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offs
 int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
                        const void* d_scalars, size_t n, uint64_t out_affine[16]);
 
+/* Asynchronous G1 MSM: _begin enqueues it and returns a ticket (0..2; three can be open per ctx), _end waits for that
+ * MSM alone and returns its result.  Calls made in between on the same ctx (b200g16_prove*, b200g16_msm_*, NTTs) run
+ * behind it on the GPU while its bucket reduction overlaps them.  For gnark's prover: pedersen ProveKnowledge
+ * (backend/groth16/bn254/prove.go, after Solve) can be begun before b200g16_prove and ended after it.
+ * The scalars (host or device) must stay unchanged until _end returns.
+ * Not allowed between b200g16_prove_begin_dev and _end_dev (B200G16_ERR_STATE). */
+int b200g16_msm_g1_begin(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                         const uint64_t* scalars, size_t n, int* ticket);
+int b200g16_msm_g1_begin_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
+                             const void* d_scalars, size_t n, int* ticket);
+int b200g16_msm_g1_end(b200g16_ctx* ctx, int ticket, uint64_t out_affine[8]);
+
 /* ---- Fr NTT / computeH -------------------------------------------------------------- */
 /* In-place transform of 2^log2n fr.Elements (HOST memory) with gnark-crypto's conventions.
  * Replaces ecc/bn254/fr/fft (*Domain).FFT (inverse=0) / (*Domain).FFTInverse (inverse=1)

@@ -215,22 +215,45 @@ func Prove(r1cs *cs.R1CS, pk *ProvingKey, fullWitness witness.Witness, opts ...b
 	wireValues := []fr.Element(solution.W)
 
 	// Pedersen proofs of knowledge (gnark: ProveKnowledge per key): one MSM per commitment on BasisExpSigma,
-	// folded with the "G16-BSB22" challenge exactly as upstream
+	// folded with the "G16-BSB22" challenge exactly as upstream.  Nothing before the fold needs their results, so the
+	// first three are only ENQUEUED here (b200g16_msm_g1_begin: three tickets per ctx) and collected after
+	// b200g16_prove — their bucket reductions run under the prove's first MSM; further keys take the synchronous call.
 	poks := make([]curve.G1Affine, len(pk.CommitmentKeys))
+	tickets := make([]C.int, len(pk.CommitmentKeys))
 	for i := range pk.CommitmentKeys {
+		tickets[i] = -1
+		if i < 3 && len(privateCommittedValues[i]) > 0 {
+			v := privateCommittedValues[i]
+			if err = call(func() C.int {
+				return C.b200g16_msm_g1_begin(pk.ctx, pk.pedSigma[i], 0, u64(unsafe.Pointer(&v[0])), C.size_t(len(v)), &tickets[i])
+			}); err != nil {
+				return nil, err
+			}
+			continue
+		}
 		if poks[i], err = msmG1(pk.ctx, pk.pedSigma[i], privateCommittedValues[i]); err != nil {
 			return nil, err
 		}
 	}
+	collectPoks := func() error {
+		for i, t := range tickets {
+			if t < 0 {
+				continue
+			}
+			if err := call(func() C.int { return C.b200g16_msm_g1_end(pk.ctx, t, u64(unsafe.Pointer(&poks[i]))) }); err != nil {
+				return err
+			}
+			tickets[i] = -1
+		}
+		return nil
+	}
+	defer collectPoks() // an early return must not leave tickets open
 	commitmentsSerialized := make([]byte, fr.Bytes*len(commitmentInfo))
 	for i := range commitmentInfo {
 		copy(commitmentsSerialized[fr.Bytes*i:], wireValues[commitmentInfo[i].CommitmentIndex].Marshal())
 	}
 	challenge, err := fr.Hash(commitmentsSerialized, []byte("G16-BSB22"), 1)
 	if err != nil {
-		return nil, err
-	}
-	if _, err = proof.CommitmentPok.Fold(poks, challenge[0], ecc.MultiExpConfig{NbTasks: 1}); err != nil {
 		return nil, err
 	}
 
@@ -252,6 +275,12 @@ func Prove(r1cs *cs.R1CS, pk *ProvingKey, fullWitness witness.Witness, opts ...b
 			u64(unsafe.Pointer(&_r)), u64(unsafe.Pointer(&_s)), &out, nil)
 	})
 	if err != nil {
+		return nil, err
+	}
+	if err = collectPoks(); err != nil {
+		return nil, err
+	}
+	if _, err = proof.CommitmentPok.Fold(poks, challenge[0], ecc.MultiExpConfig{NbTasks: 1}); err != nil {
 		return nil, err
 	}
 	proof.Ar = *(*curve.G1Affine)(unsafe.Pointer(&out.ar))

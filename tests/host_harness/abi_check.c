@@ -30,6 +30,12 @@ int main(void) {
   if (b200g16_group_size(NULL) != 0 || b200g16_group_ctx(NULL, 0) != NULL) return 18;
   if (b200g16_host_register(NULL, 0) != B200G16_ERR_ARG || b200g16_host_unregister(NULL) != B200G16_ERR_ARG) return 19;
   if (b200g16_group_msm_g1(NULL, NULL, NULL, 0, out) != B200G16_ERR_ARG) return 20;
+  {
+    int ticket = -1; /* asynchronous MSM: argument checks answer without a device */
+    if (b200g16_msm_g1_begin(NULL, NULL, 0, NULL, 0, &ticket) != B200G16_ERR_ARG) return 24;
+    if (b200g16_msm_g1_begin_dev(NULL, NULL, 0, NULL, 0, &ticket) != B200G16_ERR_ARG) return 25;
+    if (b200g16_msm_g1_end(NULL, 0, out) != B200G16_ERR_ARG) return 26;
+  }
   if (b200g16_group_pk_upload(NULL, &d, NULL) != B200G16_ERR_ARG) return 21;
   if (b200g16_group_prove(NULL, NULL, NULL, 0, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL) != B200G16_ERR_ARG) return 22;
   b200g16_group_bases_free(NULL);

@@ -259,6 +259,44 @@ def test_external_known_answer_eip196_double_generator(ctx):
     assert np.array_equal(lib.g1_add(gen, gen), exp)
 
 
+def test_msm_g1_async_begin_end(ctx, rng):
+    """b200g16_msm_g1_begin / _end (gnark's pedersen ProveKnowledge enqueued ahead of Prove): results equal the
+    synchronous call whatever runs in between — other MSMs of both groups, tickets ended out of order — from host and
+    from device scalars; a fourth open ticket and an unknown ticket are refused."""
+    import torch
+    from gnark_whir_b200 import lib
+    n = 5000
+    ks, pts = _rand_points(rng, 64)
+    pts = (pts * (n // 64 + 1))[:n]
+    bases = ctx.upload_g1(bn.g1_to_array(pts))
+    g2 = ctx.fixed_base_mul(bn.g2_to_array([bn.G2_GEN])[0], bn.fr_to_mont_array([rng.randrange(1, R) for _ in range(300)]),
+                            group=2, resident=True)
+    arrs = [bn.fr_to_mont_array([rng.randrange(R) for _ in range(n)]) for _ in range(3)]
+    expect = [ctx.msm(bases, a) for a in arrs]
+    g2s = bn.fr_to_mont_array([rng.randrange(R) for _ in range(300)])
+    g2_expect = ctx.msm(g2, g2s)
+    dev = torch.from_numpy(arrs[2].view(np.int64)).cuda()
+    t0 = ctx.msm_begin(bases, arrs[0])
+    t1 = ctx.msm_begin(bases, arrs[1], offset=0, n=n)
+    t2 = ctx.msm_begin(bases, dev.data_ptr(), n=n)
+    assert sorted((t0, t1, t2)) == [0, 1, 2]
+    with pytest.raises(lib.B200Error):
+        ctx.msm_begin(bases, arrs[0])                     # all three tickets open
+    assert np.array_equal(ctx.msm(g2, g2s), g2_expect)    # synchronous calls in between run behind the open ones
+    assert np.array_equal(ctx.msm(bases, arrs[1]), expect[1])
+    assert np.array_equal(ctx.msm_end(t2), expect[2])
+    assert np.array_equal(ctx.msm_end(t0), expect[0])
+    t3 = ctx.msm_begin(bases, arrs[2])                    # a released ticket is handed out again
+    assert np.array_equal(ctx.msm_end(t1), expect[1])
+    assert np.array_equal(ctx.msm_end(t3), expect[2])
+    with pytest.raises(lib.B200Error):
+        ctx.msm_end(t3)                                   # not open any more
+    t4 = ctx.msm_begin(bases, arrs[0][:0])                # empty MSM: infinity
+    assert not ctx.msm_end(t4).any()
+    bases.free()
+    g2.free()
+
+
 def test_concurrent_calls_on_one_context(ctx, rng):
     """gnark calls MultiExp from several goroutines at once (SURVEY §8b threading): calls on one ctx from
     several OS threads must serialise inside the library and each return its own result."""
