@@ -305,6 +305,9 @@ def prove_bench(ctx, D, rank, L, args, steps, warmup, want_e2e, want_cpu):
         return xch1.combine(points, group) if world > 1 else points
 
     def step():
+        if dh is None:
+            aa, bb, cc = (t.clone() for t in d_abc)                                             # computeH works in place
+            torch.cuda.synchronize()
         com = gather_sum(ctx.msm(ped[0], d_com.data_ptr(), n=c_hi - c_lo))                     # Commit (inside Solve)
         # ProveKnowledge: enqueued ahead of the prove (nothing in between needs its result), collected after it
         tk = ctx.msm_begin(ped[1], d_com.data_ptr(), n=c_hi - c_lo)
@@ -315,8 +318,6 @@ def prove_bench(ctx, D, rank, L, args, steps, warmup, want_e2e, want_cpu):
             proof = ctx.prove_finish(key.handle, sums["msm_a"], sums["msm_b1"], sums["msm_k"], sums["msm_z"], sums["msm_b2"], rr, ss)
             pok = gather_sum(ctx.msm_end(tk))
             return proof, com, pok, None
-        aa, bb, cc = (t.clone() for t in d_abc)                                                 # computeH works in place
-        torch.cuda.synchronize()
         if world == 1:
             proof = ctx.prove_dev(key.handle, d_w.data_ptr(), aa.data_ptr(), bb.data_ptr(), cc.data_ptr(), rr, ss)
         else:
