@@ -137,6 +137,17 @@ def _check(status):
         raise B200Error(f"libb200g16 error {status}: {load().b200g16_last_error().decode()}")
 
 
+def _dp(dev_ptr):
+    """A raw device pointer for the library.  The library works on its OWN (non-blocking) streams and cannot know which
+    stream produced the data, so device-side work the caller still has in flight on torch's streams (a clone, a random
+    fill) is drained first — the C-ABI's contract for device pointers (include/b200g16.h) is "the memory is ready"."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_initialized():
+        torch.cuda.current_stream().synchronize()   # the producer's stream only: an open b200g16_msm_g1_begin keeps running
+    return _vp(int(dev_ptr))
+
+
 def _ptr(a):
     return a.ctypes.data_as(_vp)
 
@@ -450,7 +461,7 @@ class Context:
         return a
 
     def ntt_dev(self, d_ptr, log2n, batch=1, inverse=False, coset=False, decimation=DIF):
-        _check(load().b200g16_ntt_dev(self.h, _vp(int(d_ptr)), log2n, batch, int(inverse), int(coset), int(decimation)))
+        _check(load().b200g16_ntt_dev(self.h, _dp(d_ptr), log2n, batch, int(inverse), int(coset), int(decimation)))
 
     def compute_h(self, a, b, c, log2n):
         a, b, c = _u64(a, 4), _u64(b, 4), _u64(c, 4)
@@ -459,7 +470,7 @@ class Context:
         return h
 
     def compute_h_dev(self, d_a, d_b, d_c, log2n):
-        _check(load().b200g16_compute_h_dev(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)), log2n))
+        _check(load().b200g16_compute_h_dev(self.h, _dp(d_a), _dp(d_b), _dp(d_c), log2n))
 
     # -- Keccak (mirror keccakf.Permute, keccakSponge.Digest, VerifyMerkleTreeProofs)
     def keccak_f_batch(self, states):
@@ -468,7 +479,7 @@ class Context:
         return st
 
     def keccak_f_batch_dev(self, d_ptr, n):
-        _check(load().b200g16_keccak_f_batch_dev(self.h, _vp(int(d_ptr)), n))
+        _check(load().b200g16_keccak_f_batch_dev(self.h, _dp(d_ptr), n))
 
     def keccak_sponge_batch(self, inputs, out_len):
         """inputs: (n, in_len) uint8 -> (n, out_len) uint8"""
@@ -532,7 +543,7 @@ class Context:
     def prove_dev(self, pk, d_wires, d_a, d_b, d_c, r, s):
         r, s = _u64(r).reshape(4), _u64(s).reshape(4)
         out = ProofOut()
-        _check(load().b200g16_prove_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)),
+        _check(load().b200g16_prove_dev(self.h, pk, _dp(d_wires), _dp(d_a), _dp(d_b), _dp(d_c),
                                         _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
 
@@ -605,24 +616,24 @@ class Context:
         return c.value, w.value
 
     def h_pointwise_dev(self, d_a, d_b, d_c, log2n):
-        _check(load().b200g16_h_pointwise_dev(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c)), log2n))
+        _check(load().b200g16_h_pointwise_dev(self.h, _dp(d_a), _dp(d_b), _dp(d_c), log2n))
 
     def prove_h_dev(self, pk, d_wires, d_h, r, s):
         """prove_dev with h already computed (d_h: N elements, bit-reversed order)."""
         r, s = _u64(r).reshape(4), _u64(s).reshape(4)
         out = ProofOut()
-        _check(load().b200g16_prove_h_dev(self.h, pk, _vp(int(d_wires)), _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
+        _check(load().b200g16_prove_h_dev(self.h, pk, _dp(d_wires), _dp(d_h), _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
 
     def prove_begin_dev(self, pk, d_wires):
         """First half of a prove: the four witness MSMs are enqueued; returns without waiting."""
-        _check(load().b200g16_prove_begin_dev(self.h, pk, _vp(int(d_wires))))
+        _check(load().b200g16_prove_begin_dev(self.h, pk, _dp(d_wires)))
 
     def prove_end_dev(self, pk, d_h, r, s):
         """Second half: Z MSM over h (device pointer), wait, assemble."""
         r, s = _u64(r).reshape(4), _u64(s).reshape(4)
         out = ProofOut()
-        _check(load().b200g16_prove_end_dev(self.h, pk, _vp(int(d_h)), _ptr(r), _ptr(s), C.byref(out)))
+        _check(load().b200g16_prove_end_dev(self.h, pk, _dp(d_h), _ptr(r), _ptr(s), C.byref(out)))
         return out.as_dict()
 
     # -- computeH split over 2 / 4 / 8 ranks (CUDA IPC peer memory; see sharded.DistributedH)
@@ -637,7 +648,7 @@ class Context:
         _check(load().b200g16_dist_h_open(self.h, _ptr(a)))
 
     def dist_h_load(self, d_a, d_b, d_c):
-        _check(load().b200g16_dist_h_load(self.h, _vp(int(d_a)), _vp(int(d_b)), _vp(int(d_c))))
+        _check(load().b200g16_dist_h_load(self.h, _dp(d_a), _dp(d_b), _dp(d_c)))
 
     def dist_h_slice(self, which):
         p = load().b200g16_dist_h_slice(self.h, which)
@@ -663,7 +674,7 @@ class Context:
             _check(fn(self.h, bases.handle, offset, _ptr(sc), n, _ptr(out)))
         else:  # raw device pointer (e.g. torch tensor .data_ptr())
             fn = lib.b200g16_msm_g1_dev if bases.group == 1 else lib.b200g16_msm_g2_dev
-            _check(fn(self.h, bases.handle, offset, _vp(int(scalars)), n, _ptr(out)))
+            _check(fn(self.h, bases.handle, offset, _dp(scalars), n, _ptr(out)))
         return out
 
     def msm_begin(self, bases, scalars, offset=0, n=None):
@@ -677,7 +688,7 @@ class Context:
             self._async_keep = getattr(self, "_async_keep", {})
             self._async_keep[ticket.value] = sc
         else:
-            _check(lib.b200g16_msm_g1_begin_dev(self.h, bases.handle, offset, _vp(int(scalars)), n, C.byref(ticket)))
+            _check(lib.b200g16_msm_g1_begin_dev(self.h, bases.handle, offset, _dp(scalars), n, C.byref(ticket)))
         return ticket.value
 
     def msm_end(self, ticket):

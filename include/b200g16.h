@@ -20,7 +20,12 @@
  *   - every function returns 0 on success, a negative B200G16_ERR_* otherwise;
  *     b200g16_last_error() returns a thread-local message for the last failure.
  *   - host pointers are only read/written during the call and never retained
- *     (cgo pointer rules); device memory is owned by the ctx / bases handles.
+ *     (cgo pointer rules; the one exception, b200g16_msm_g1_begin, says so); device memory is
+ *     owned by the ctx / bases handles.
+ *   - *_dev entry points take caller-owned DEVICE pointers.  The library works on its own
+ *     non-blocking streams: the memory behind such a pointer must be READY when the call is made
+ *     (work the caller has in flight on its own streams is not waited for), and every *_dev call
+ *     except the _begin forms has finished with it on return.
  *   - a ctx is bound to one GPU; calls on one ctx are serialised internally, so it may
  *     be used from any OS thread (goroutines).  One process per GPU for multi-GPU.
  *   - there is NO CPU fallback: without a usable CUDA device b200g16_init fails.

@@ -61,6 +61,7 @@ def test_ntt_2p24_round_trips_and_linearity(ctx):
         return a
     a = rnd()
     ref = a.clone()
+    torch.cuda.synchronize()      # the library runs on its own streams: torch's fill and clone must have finished
     ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)
     assert not torch.equal(a, ref)
     ctx.ntt_dev(a.data_ptr(), L, inverse=True, decimation=lib.DIT)
@@ -81,6 +82,7 @@ def test_ntt_2p24_round_trips_and_linearity(ctx):
         out[:, j] = lo2
         carry = c1 + c2
     s = torch.from_numpy(out.view(np.int64)).cuda()
+    torch.cuda.synchronize()
     for v in (x, y, s):
         ctx.ntt_dev(v.data_ptr(), L, decimation=lib.DIF)
     # field addition of the two spectra on the host for a strided sample
@@ -104,6 +106,7 @@ def test_ntt_2p26_largest_size_definition_check_and_round_trips(ctx):
     vals = [int(x) for x in rs.integers(1, 1 << 62, size=len(pos))]
     a = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
     a[torch.tensor(pos, device="cuda")] = torch.from_numpy(bn.fr_to_mont_array(vals).view(np.int64)).cuda()
+    torch.cuda.synchronize()
     ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)          # natural in, bit-reversed out
     ks = [0, 1, 2, n // 2, n - 1] + [int(x) for x in rs.integers(0, n, size=59)]
     got = bn.fr_from_mont_array(a[torch.tensor([ontt.bitrev(k, L) for k in ks], device="cuda")].cpu().numpy().view(np.uint64))
@@ -114,6 +117,7 @@ def test_ntt_2p26_largest_size_definition_check_and_round_trips(ctx):
     a = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
     a[:, 3] &= (1 << 60) - 1
     ref = a.clone()
+    torch.cuda.synchronize()      # the library runs on its own streams: torch's fill and clone must have finished
     ctx.ntt_dev(a.data_ptr(), L, decimation=lib.DIF)
     assert not torch.equal(a, ref)
     ctx.ntt_dev(a.data_ptr(), L, inverse=True, decimation=lib.DIT)
