@@ -483,10 +483,10 @@ int msm_enqueue(b200g16_ctx* ctx, const Affine<F>* d_bases, const MsmTable* tab,
   if (l0 < 2) l0 = 2;                         // level 1 (reads the partials through the task table) is always its own kernel
   constexpr bool CAN_INL = sizeof(F) <= 32;
   const bool inl = CAN_INL && reduce_inline_default() >= 1, inl_tail = CAN_INL && reduce_inline_default() >= 2;
-  // CTA size of the grid-wide levels.  G2 (~180 registers per thread, the out-of-line addition): experiment knob
-  // B200G16_G2_REDUCE_BLOCK (read once)
-  static const unsigned g2_block = [] { const char* e = getenv("B200G16_G2_REDUCE_BLOCK"); return e ? (unsigned)atoi(e) : 128u; }();
-  const unsigned rb = CAN_INL ? 128u : g2_block;
+  // CTA size of the grid-wide levels.  (G2, ~180 registers per thread with the out-of-line addition: 32 / 64 / 96 / 128
+  // threads per CTA measure 1.75 / 1.77 / 2.07 / 1.78 ms for the whole reduction at c = 20, profiles/r02w_g2_reduce_block.jsonl
+  // — occupancy is not its lever.)
+  constexpr unsigned rb = 128u;
   const unsigned g1 = cdiv((size_t)cfg.Wr * (cfg.nbw >> 1), rb);
   if (inl) k_reduce_first<F, CAN_INL><<<g1, rb, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);
   else k_reduce_first<F, false><<<g1, rb, 0, tail>>>(partials, counts, task_off, (uint32_t)cfg.Wr, cfg.nbw, chunks);

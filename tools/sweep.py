@@ -188,7 +188,7 @@ def reduce_ab(ctx):
             if best is None or sum(ph) < sum(best):
                 best = ph
         emit(config="msm_reduce_ab", group="G2" if g2 else "G1", reduce_inline=os.environ.get("B200G16_REDUCE_INLINE", "default"),
-             g2_reduce_block=os.environ.get("B200G16_G2_REDUCE_BLOCK", "default"), log2n=logn,
+             log2n=logn,
              device_ms=round(sum(best), 3), phases_ms=[round(x, 3) for x in best], bit_exact_vs_oracle=ok)
         bases.free()
 
