@@ -216,7 +216,8 @@ int b200g16_msm_g2_dev(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offs
  * MSM alone and returns its result.  Calls made in between on the same ctx (b200g16_prove*, b200g16_msm_*, NTTs) run
  * behind it on the GPU while its bucket reduction overlaps them.  For gnark's prover: pedersen ProveKnowledge
  * (backend/groth16/bn254/prove.go, after Solve) can be begun before b200g16_prove and ended after it.
- * The scalars (host or device) must stay unchanged until _end returns.
+ * The scalars (host or device) must stay valid and unchanged until _end returns — the one place where the library
+ * keeps a host pointer beyond a call (from Go: runtime.Pinner around _begin .. _end).
  * Not allowed between b200g16_prove_begin_dev and _end_dev (B200G16_ERR_STATE). */
 int b200g16_msm_g1_begin(b200g16_ctx* ctx, const b200g16_bases* bases, size_t offset,
                          const uint64_t* scalars, size_t n, int* ticket);

@@ -220,10 +220,13 @@ func Prove(r1cs *cs.R1CS, pk *ProvingKey, fullWitness witness.Witness, opts ...b
 	// b200g16_prove — their bucket reductions run under the prove's first MSM; further keys take the synchronous call.
 	poks := make([]curve.G1Affine, len(pk.CommitmentKeys))
 	tickets := make([]C.int, len(pk.CommitmentKeys))
+	var pokPin runtime.Pinner // _begin keeps reading the scalars after it returns (registered memory is copied asynchronously)
+	defer pokPin.Unpin()
 	for i := range pk.CommitmentKeys {
 		tickets[i] = -1
 		if i < 3 && len(privateCommittedValues[i]) > 0 {
 			v := privateCommittedValues[i]
+			pokPin.Pin(&v[0])
 			if err = call(func() C.int {
 				return C.b200g16_msm_g1_begin(pk.ctx, pk.pedSigma[i], 0, u64(unsafe.Pointer(&v[0])), C.size_t(len(v)), &tickets[i])
 			}); err != nil {
