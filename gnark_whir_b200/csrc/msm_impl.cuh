@@ -18,7 +18,7 @@
 //                 XYZZ adds (10 modmul) on the integer pipe; next point prefetched during the add
 //   ---- "tail", on a second stream under the next MSM's work above ----
 //   k_merge_pass  fan-in-4 tree over the partials of split buckets
-//   k_reduce_first / _level / _weights, k_sum_pass  log-depth tree for sum_b (b+1) B_b (bit decomposition of the
+//   k_reduce_first / _level / _tail  log-depth tree for sum_b (b+1) B_b (bit decomposition of the
 //                 weights: 2 additions per bucket in total, dependency depth c instead of a running-sum chain)
 //   host          Horner over the window sums + one inversion -> affine
 //
@@ -140,11 +140,12 @@ __global__ void __launch_bounds__(128) k_merge_pass(XYZZ<F>* __restrict__ partia
 // set "bit n-l set" of the folded index and becomes region j = l at offset 2^(n-l) — and halves every older
 // region in place.  Before level l all l regions have 2^(n-l+1) items, so a level is l * 2^(n-l) independent
 // additions, 2 * 2^n in total (the running sum's count), and the dependency depth is n additions instead of
-// ~2 * chunk + 1.5 c.  Afterwards A[0] = G and A[2^m] = U_m; k_reduce_weights scales them by 2^m (m doublings,
-// one thread each) and the fan-in-4 sum passes below add the n + 1 terms.
+// ~2 * chunk + 1.5 c.  Afterwards A[0] = G and A[2^m] = U_m; the tail kernel (k_reduce_tail) scales them by 2^m
+// (m doublings, one thread each) and adds the n + 1 terms by a halving tree.
+//
 // INL: the addition is expanded in place with both operands in registers (like k_accumulate's mixed addition: no stack
-// copy of the accumulator, every load issued up front) instead of the out-of-line routine.  G1 only — the expanded Fp2
-// code does not fit the instruction cache.  Experiment knob: B200G16_REDUCE_INLINE=0/1 (read once).
+// copy of the accumulator, every load issued up front) instead of the out-of-line routine.  G1 only — two Fp2 points
+// (128 registers) plus the addition's temporaries do not fit a thread.  Experiment knob: B200G16_REDUCE_INLINE (read once).
 inline int reduce_inline_default() {   // 0: out of line, 1: the grid-wide levels, 2: also the one-CTA tail
   static const int v = [] { const char* e = getenv("B200G16_REDUCE_INLINE"); return e ? atoi(e) : 2; }();
   return v;
@@ -183,19 +184,6 @@ __global__ void __launch_bounds__(128, INL ? 4 : 0) k_reduce_level(XYZZ<F>* __re
     a.add(p[s]);
   }
   p[0] = a;
-}
-
-// terms[w][m] = 2^m * U_m (m < n), terms[w][n] = G
-template <class F>
-__global__ void __launch_bounds__(32) k_reduce_weights(const XYZZ<F>* __restrict__ A, uint32_t Wr, uint32_t nbw, uint32_t n,
-                                                        XYZZ<F>* __restrict__ terms) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= Wr * (n + 1)) return;
-  const uint32_t w = g / (n + 1), m = g % (n + 1);
-  XYZZ<F> v = A[(size_t)w * nbw + (m == n ? 0u : (1u << m))];
-  if (m < n)
-    for (uint32_t k = 0; k < m; k++) v.dbl();
-  terms[g] = v;
 }
 
 // The END of the tree in one CTA per window: once a level fits 512 threads (l * 2^(n-l) <= 512) the remaining
@@ -297,23 +285,6 @@ __global__ void __launch_bounds__(256) k_merge_heavy(XYZZ<F>* __restrict__ parti
     }
     __syncthreads();
   }
-}
-
-// plain sums, fan-in 4: out[w][g] = sum_{j<4} in[w][4 g + j]   (len_in items per window, thread per g);
-// applied until one item per window is left (3 dependent additions per level)
-constexpr uint32_t SUM_FANIN = 4;
-
-template <class F>
-__global__ void __launch_bounds__(128) k_sum_pass(const XYZZ<F>* __restrict__ in, uint32_t len_in, uint32_t len_out,
-                                                   uint32_t total_out, XYZZ<F>* __restrict__ out) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total_out) return;
-  uint32_t w = g / len_out, k = g % len_out;
-  const XYZZ<F>* src = in + (size_t)w * len_in;
-  uint32_t lo = k * SUM_FANIN, hi = lo + SUM_FANIN < len_in ? lo + SUM_FANIN : len_in;
-  XYZZ<F> acc = src[lo];
-  for (uint32_t j = lo + 1; j < hi; j++) acc.add(src[j]);
-  out[g] = acc;
 }
 
 }  // namespace b200
