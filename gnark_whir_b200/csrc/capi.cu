@@ -271,8 +271,6 @@ void b200g16_destroy(b200g16_ctx* ctx) {
   for (int i = 0; i < MSM_SETS; i++) { cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_tail[i]); }
   for (auto& ev : ctx->ev_copy) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_slot) cudaEventDestroy(ev);
-  for (auto& ev : ctx->trace_ev)
-    if (ev) cudaEventDestroy(ev);
   h2d_stager_release(ctx);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->tail_stream);

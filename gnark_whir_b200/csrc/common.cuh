@@ -155,7 +155,6 @@ struct b200g16_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D of host scalars, pipelined against the MSM of the previous piece
   cudaEvent_t ev_copy[8] = {};
   cudaEvent_t ev_front[b200::MSM_SETS] = {}, ev_tail[b200::MSM_SETS] = {};
-  cudaEvent_t trace_ev[16] = {};    // B200G16_SORT_TRACE only (msm_sort_phase), created on first use
   cudaEvent_t ev_slot[8] = {};      // ev_slot[s]: the window sums of the MSM enqueued into result slot s have reached pinned memory
   bool tail_pending[b200::MSM_SETS] = {};
   int msm_parity = 0;               // next rotating buffer set (0 .. MSM_SETS-1)

@@ -376,10 +376,10 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   // B200G16_SORT_TRACE=1: an event after every operation of this phase, printed (and the stream drained) at its end —
   // where the phase's time goes inside a real call, launch gaps included (tools/sweep.py --reduce-ab)
   static const bool trace = getenv("B200G16_SORT_TRACE") != nullptr;
-  cudaEvent_t* tev = ctx->trace_ev;   // per ctx: events belong to the device they were created on
+  static cudaEvent_t tev[16];
+  static bool tev_made = false;
   int nt = 0;
-  if (trace && !tev[0])
-    for (int i = 0; i < 16; i++) cudaEventCreate(&tev[i]);
+  if (trace && !tev_made) { for (auto& e : tev) cudaEventCreate(&e); tev_made = true; }
   auto tr = [&]() { if (trace && nt < 16) cudaEventRecord(tev[nt++], st); };
   mark();
   tr();
