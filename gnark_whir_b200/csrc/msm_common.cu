@@ -374,7 +374,8 @@ int msm_sort_phase(b200g16_ctx* ctx, const MsmCfg& cfg, const Fr* d_scalars, uin
   cudaStream_t st = ctx->stream;
   auto mark = [&]() { if (ev && *ev < 18) cudaEventRecord(ctx->ev[(*ev)++], st); };
   // B200G16_SORT_TRACE=1: an event after every operation of this phase, printed (and the stream drained) at its end —
-  // where the phase's time goes inside a real call, launch gaps included (tools/sweep.py --reduce-ab)
+  // where the phase's time goes inside a real call, launch gaps included (tools/sweep.py --reduce-ab).  One set of
+  // events per process: a single-device debugging aid, not for b200g16_group_* runs.
   static const bool trace = getenv("B200G16_SORT_TRACE") != nullptr;
   static cudaEvent_t tev[16];
   static bool tev_made = false;
